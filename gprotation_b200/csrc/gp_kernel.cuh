@@ -1,0 +1,648 @@
+// gp_kernel.cuh -- fused covariance synthesis + blocked fp64 Cholesky + forward solve, sm_100a.
+//
+// One persistent CTA (512 threads, 16 warps) per SM pulls (walker, chunk) problems from a
+// global queue.  For a problem of n points (padded with identity to Npad = T*128):
+//
+//   for block column J = 0..T-1                         (left-looking, 128 x 128 blocks)
+//     S_JJ = K_JJ - sum_{k<J} L_Jk L_Jk^T               DMMA, operands streamed by TMA bulk copies
+//     L_JJ, W = L_JJ^{-1}  (8-wide micro panels, DMMA)  in shared memory, one sweep gives both
+//     z_J = W ytilde_J ; quad += |z_J|^2 ; logdet += 2 sum log diag(L_JJ)
+//     for I > J:
+//        S_IJ = K_IJ - sum_{k<J} L_Ik L_Jk^T            DMMA (the N^3/3 term)
+//        L_IJ = S_IJ W^T                                DMMA (TRSM as a GEMM with the inverse)
+//        ytilde_I -= L_IJ z_J                           right-looking forward solve, fused
+//        store L_IJ (fragment-major) to the slot's scratch
+//   lnlike = -1/2 (quad + logdet + n log 2 pi)
+//
+// K is never materialised: each 128 x 128 tile of it is synthesised from the time stamps and
+// the five hyper-parameters directly into the DMMA accumulator registers (C-fragment layout)
+// at the first (and only) touch of that tile.  Reference arithmetic being replaced:
+// gprot/model.py:328-356 (george kernel build + HODLR factor + lnlikelihood).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+namespace gprot {
+
+constexpr int BS = 128;           // block edge
+constexpr int NT = 512;           // threads per CTA
+constexpr int SLAB = 2048;        // doubles in one 128 x 16 operand slab (16 KB)
+constexpr int BLKD = 16384;       // doubles in one 128 x 128 block (8 slabs)
+constexpr int STAGES = 4;         // TMA pipeline depth; one stage = A slab + B slab = 32 KB
+constexpr int LDM = 132;          // row pitch of the diagonal-block workspace (== 4 mod 16: conflict-free fragments)
+constexpr int REGION_A = 128 * LDM;   // doubles; >= STAGES * 2 * SLAB
+constexpr int W_DOUBLES = 9216;   // packed fragment-major lower triangle of W (72 KB)
+
+struct Hyp {
+    double A, L, G, S, P;   // exp(theta)
+    double hl;              // 0.5 / L
+    double thr;             // DBL_EPSILON * L : WhiteKernel fires where d*d/L < DBL_EPSILON
+};
+
+struct Smem {
+    double regionA[REGION_A];     // TMA stages | S_IJ staging (fragment-major) | diagonal workspace M (row-major)
+    double W[W_DOUBLES];          // L_JJ^{-1}, B-operand fragments, rows c >= 16*slab only
+    double red[4 * BS];           // cross-warp partial sums of L_IJ z_J
+    double zs[BS];                // z_J
+    double yj[BS];                // ytilde_J
+    double dinv[BS];              // 1 / diag(L_JJ)
+    double wt[64];                // inverse of the current 8 x 8 diagonal tile
+    Hyp hyp;
+    double quad;
+    unsigned long long full[STAGES];
+    unsigned long long empty[STAGES];
+    int prob;
+    int fail;
+};
+
+struct Params {
+    // packed light-curve arena (all registered chunks back to back)
+    const double* t;
+    const double* y;
+    const double* yerr;
+    const long long* chunk_off;   // [nchunks] offset of the chunk in the arena
+    const int* chunk_n;           // [nchunks]
+    const double* chunk_mingap2;  // [nchunks] min squared gap between distinct stamps (white-kernel test)
+    const double* theta;          // [B,5]
+    const int* prob_theta;        // [nprob] row of theta
+    const int* prob_chunk;        // [nprob] chunk index
+    double* prob_out;             // [nprob]
+    int nprob;
+    int* counter;                 // work queue head
+    double* lscratch;             // per-slot factor scratch
+    size_t lslot_stride;          // doubles
+    double* vscratch;             // per-slot vectors: sin, cos, diag, ytilde (4 * npad_max)
+    int npad_max;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// order generic-proxy accesses (st.global / ld.shared / st.shared) before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---------------------------------------------------------------- layouts
+// Fragment-major operand layout.  A 128 x 16 slab is stored as [row group 16][k pair 2][lane 32][2]:
+// lane = (r&7)*4 + (k&3) is the DMMA A/B fragment lane, the pair holds k-quads 2*kp and 2*kp+1, so one
+// LDS.128 per lane fetches the fragments of two consecutive m8n8k4 steps, bank-conflict free.
+__device__ __forceinline__ int frag_off(int r, int kk) {   // r in [0,128), kk in [0,16)
+    return (r >> 3) * 128 + ((kk >> 3) & 1) * 64 + (((r & 7) << 2) + (kk & 3)) * 2 + ((kk >> 2) & 1);
+}
+__device__ __forceinline__ int w_slab_off(int s) { return 128 * s * (17 - s); }   // slab s keeps row groups 2s..15
+
+// Store a warp's 32 x 32 C-fragment tile (acc[mi][ni][e] at row 8mi+g, col 8ni+2q+e) into a fragment-major
+// block at tile origin (row0, col0), optionally negated.  Lanes q and q^2 hold neighbouring doubles of the
+// destination, so one shuffle turns 32 scalar stores into 16 16-byte stores.
+template <bool NEG>
+__device__ __forceinline__ void store_tile_frag(double* blk, const double (&acc)[4][4][2], int row0, int col0, int lane) {
+    const int g = lane >> 2, q = lane & 3, h = q >> 1;
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+        const int c = col0 + 8 * ni;                       // multiple of 8
+        const int slab = c >> 4, kp = (c >> 3) & 1;
+        double* base = blk + slab * SLAB + kp * 64 + ((g << 2) + ((q & 1) << 1) + h) * 2;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+            double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
+            if (NEG) { v0 = -v0; v1 = -v1; }
+            const double send = h ? v0 : v1;
+            const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            double2 o;
+            o.x = h ? recv : v0;
+            o.y = h ? v1 : recv;
+            const int rg = (row0 >> 3) + mi;
+            *reinterpret_cast<double2*>(base + rg * 128) = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- covariance synthesis
+// EXACT: george's operation order, entry by entry (oracle/gp_oracle.py kernel_matrix).
+// fast : sin(pi (ti-tj)/P) = si*cj - ci*sj from per-point phases reduced in double-double, one exp.
+template <bool EXACT>
+__device__ __forceinline__ double kentry(double ti, double tj, double si, double ci, double sj, double cj, const Hyp& h) {
+    const double d = ti - tj;
+    if (EXACT) {
+        const double r2 = __ddiv_rn(__dmul_rn(d, d), h.L);
+        const double s = sin(__ddiv_rn(__dmul_rn(M_PI, d), h.P));
+        const double e1 = exp(__dmul_rn(-0.5, r2));
+        const double e2 = exp(__dmul_rn(__dmul_rn(-h.G, s), s));
+        return __dmul_rn(__dmul_rn(h.A, e1), e2);
+    } else {
+        const double sn = si * cj - ci * sj;
+        return h.A * exp(fma(-h.G * sn, sn, -(d * d) * h.hl));
+    }
+}
+
+// acc <- -K(I,J) for this warp's 32 x 32 tile.  GENERAL handles the diagonal (white noise + yerr),
+// identity padding beyond n, and coincident time stamps off the diagonal.
+template <bool EXACT, bool GENERAL>
+__device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], int row0, int col0, int n, const double* __restrict__ t,
+                                           const double* vs, const double* vc,
+                                           const double* vd, const Hyp& h, bool white_off, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    double ti[4], si[4], ci[4];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        const int r = row0 + 8 * mi + g;
+        ti[mi] = t[GENERAL ? min(r, n - 1) : r];
+        si[mi] = vs[r];
+        ci[mi] = vc[r];
+    }
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int c = col0 + 8 * ni + 2 * q + e;
+            const double tj = t[GENERAL ? min(c, n - 1) : c];
+            const double sj = vs[c], cj = vc[c];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) {
+                double k = kentry<EXACT>(ti[mi], tj, si[mi], ci[mi], sj, cj, h);
+                if (GENERAL) {
+                    const int r = row0 + 8 * mi + g;
+                    const double d = ti[mi] - tj;
+                    if (r == c) k = (k + h.S) + vd[r];
+                    else if (white_off && d * d < h.thr) k += h.S;
+                    if (r >= n || c >= n) k = (r == c) ? 1.0 : 0.0;
+                }
+                acc[mi][ni][e] = -k;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- streamed accumulation  acc += A * B^T
+// The producer (thread 0) keeps STAGES-1 slabs in flight.  `it` is the CTA-wide pipeline iteration counter:
+// stage = it % STAGES, parity = (it / STAGES) & 1, identical in every thread.
+template <bool DIAG>
+__device__ __forceinline__ void issue_stage(Smem& sm, uint32_t it, const double* arow, const double* brow, int i) {
+    const uint32_t st = it % STAGES;
+    mbar_wait(&sm.empty[st], ((it / STAGES) & 1) ^ 1);
+    double* dst = sm.regionA + st * (2 * SLAB);
+    mbar_expect_tx(&sm.full[st], (DIAG ? 1 : 2) * SLAB * 8);
+    tma_load(dst, arow + (size_t)i * SLAB, SLAB * 8, &sm.full[st]);
+    if (!DIAG) tma_load(dst + SLAB, brow + (size_t)i * SLAB, SLAB * 8, &sm.full[st]);
+}
+
+template <bool DIAG>
+__device__ __forceinline__ void prologue(Smem& sm, uint32_t it, const double* arow, const double* brow, int niter) {
+    const int np = niter < STAGES - 1 ? niter : STAGES - 1;
+    for (int i = 0; i < np; i++) issue_stage<DIAG>(sm, it + i, arow, brow, i);
+}
+
+template <bool DIAG>
+__device__ __forceinline__ void accumulate(Smem& sm, double (&acc)[4][4][2], uint32_t& it, const double* arow, const double* brow,
+                                           int niter, int wr, int wc, int lane, bool active) {
+    const int tid = threadIdx.x;
+    for (int i = 0; i < niter; i++, it++) {
+        if (tid == 0 && i + STAGES - 1 < niter) issue_stage<DIAG>(sm, it + STAGES - 1, arow, brow, i + STAGES - 1);
+        const uint32_t st = it % STAGES;
+        mbar_wait(&sm.full[st], (it / STAGES) & 1);
+        if (active) {
+            const double* As = sm.regionA + st * (2 * SLAB);
+            const double* Bs = DIAG ? As : As + SLAB;
+#pragma unroll
+            for (int kp = 0; kp < 2; kp++) {
+                double2 a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+    }
+}
+
+// ---------------------------------------------------------------- diagonal block: L_JJ and W = L_JJ^{-1} in one sweep
+// Workspace M (row-major, pitch LDM) holds S_JJ in its lower triangle and zeros above.  Eliminating 8 columns at a
+// time, the lower triangle becomes L and -- treating the rows above the diagonal as the identity appended below S --
+// the strict upper triangle becomes L^{-T} (M[i][c] = W[c][i]); 1/diag(L) goes to sm.dinv.
+//
+// (i)   warp 0 factors the 8 x 8 diagonal tile and inverts it in registers;
+// (ii)  every other tile row of the panel is multiplied by the tile inverse (2 DMMAs per tile);
+// (iii) all tiles right of the panel receive the rank-8 update (2 DMMAs per tile).
+__device__ __forceinline__ void tile8_factor(Smem& sm, int p, int lane, double& logdet) {
+    double* Mp = sm.regionA + (8 * p) * LDM + 8 * p;
+    double l[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) l[a][b] = Mp[a * LDM + b];
+    double rinv[8];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const double d = l[j][j];
+        if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
+        const double ljj = sqrt(d);
+        const double ri = 1.0 / ljj;
+        l[j][j] = ljj;
+        rinv[j] = ri;
+#pragma unroll
+        for (int a = j + 1; a < 8; a++) l[a][j] *= ri;
+#pragma unroll
+        for (int a = j + 1; a < 8; a++)
+#pragma unroll
+            for (int b = j + 1; b <= a; b++) l[a][b] = fma(-l[a][j], l[b][j], l[a][b]);
+    }
+    // column b = lane & 7 of the inverse: w_b = 1/l_bb, w_a = -(sum_{m<a} l_am w_m)/l_aa (w_m = 0 for m < b)
+    const int b = lane & 7;
+    double w[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < a; m++) s = fma(l[a][m], w[m], s);
+        w[a] = (a == b) ? rinv[a] : ((a > b) ? -rinv[a] * s : 0.0);
+    }
+    __syncwarp();
+    if (lane < 8) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            sm.wt[a * 8 + b] = w[a];                        // W_pp[a][b], zeros above the diagonal
+            if (a > b) Mp[b * LDM + a] = w[a];              // strict upper of the tile: W_pp^T
+        }
+        sm.dinv[8 * p + b] = w[b];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+            if (a == b) {
+#pragma unroll
+                for (int c = 0; c <= a; c++) Mp[a * LDM + c] = l[a][c];
+            }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; a++) logdet += log(l[a][a]);
+        if (bad) sm.fail = 1;
+    }
+}
+
+__device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, double& logdet) {
+    const int g = lane >> 2, q = lane & 3;
+    double* M = sm.regionA;
+    for (int p = 0; p < 16; p++) {
+        const int P0 = 8 * p;
+        if (warp == 0) tile8_factor(sm, p, lane, logdet);
+        __syncthreads();
+        // (ii) tile row `warp` of the panel: X = M(warp, p) * W_pp^T
+        if (warp != p) {
+            double* row = M + (8 * warp + g) * LDM + P0;
+            const double a0 = row[q], a1 = row[q + 4];
+            const double b0 = sm.wt[g * 8 + q], b1 = sm.wt[g * 8 + q + 4];
+            double c0 = 0.0, c1 = 0.0;
+            dmma(c0, c1, a0, b0);
+            dmma(c0, c1, a1, b1);
+            __syncwarp();
+            *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
+        }
+        __syncthreads();
+        // (iii) rank-8 update of tiles (R, C), C > p, R in [0..p] (inverse rows) or [C..15] (Schur complement)
+        const int ncol = 15 - p;
+        const int nrect = (p + 1) * ncol;
+        const int ntask = nrect + ncol * (ncol + 1) / 2;
+        for (int task = warp; task < ntask; task += 16) {
+            int R, C;
+            if (task < nrect) {
+                R = task / ncol;
+                C = p + 1 + task % ncol;
+            } else {
+                const int u = task - nrect;
+                int i = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
+                while ((i + 1) * (i + 2) / 2 <= u) i++;
+                while (i * (i + 1) / 2 > u) i--;
+                R = p + 1 + i;
+                C = p + 1 + (u - i * (i + 1) / 2);
+            }
+            double a0, a1;
+            if (R == p) {                                   // rows of the diagonal tile act through W_pp^T
+                a0 = sm.wt[q * 8 + g];
+                a1 = sm.wt[(q + 4) * 8 + g];
+            } else {
+                const double* ar = M + (8 * R + g) * LDM + P0;
+                a0 = ar[q];
+                a1 = ar[q + 4];
+            }
+            const double* br = M + (8 * C + g) * LDM + P0;
+            const double b0 = br[q], b1 = br[q + 4];
+            double2* cp = reinterpret_cast<double2*>(M + (8 * R + g) * LDM + 8 * C + 2 * q);
+            double2 c = *cp;
+            dmma(c.x, c.y, -a0, b0);
+            dmma(c.x, c.y, -a1, b1);
+            *cp = c;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <bool EXACT>
+__global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp >> 2, wc = ((warp & 3) - (warp >> 2)) & 3;   // skewed so each scheduler sees every wc
+    const int g = lane >> 2, q = lane & 3;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], 16);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t it = 0;   // pipeline iteration counter (uniform across the CTA)
+    double* const lbase = prm.lscratch + (size_t)blockIdx.x * prm.lslot_stride;
+    double* const vs = prm.vscratch + (size_t)blockIdx.x * 4 * prm.npad_max;
+    double* const vc = vs + prm.npad_max;
+    double* const vd = vc + prm.npad_max;
+    double* const yw = vd + prm.npad_max;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            sm.prob = atomicAdd(prm.counter, 1);
+            sm.fail = 0;
+            sm.quad = 0.0;
+        }
+        __syncthreads();
+        const int prob = sm.prob;
+        if (prob >= prm.nprob) break;
+
+        const int chunk = prm.prob_chunk[prob];
+        const int n = prm.chunk_n[chunk];
+        const long long off = prm.chunk_off[chunk];
+        const double* __restrict__ t = prm.t + off;
+        const double* __restrict__ y = prm.y + off;
+        const double* __restrict__ yerr = prm.yerr + off;
+        const double* th = prm.theta + 5 * (size_t)prm.prob_theta[prob];
+        const int T = (n + BS - 1) / BS;
+        const int npad = T * BS;
+
+        if (tid == 0) {
+            Hyp h;
+            h.A = exp(th[0]); h.L = exp(th[1]); h.G = exp(th[2]); h.S = exp(th[3]); h.P = exp(th[4]);
+            h.hl = 0.5 / h.L;
+            h.thr = DBL_EPSILON * h.L;
+            sm.hyp = h;
+        }
+        __syncthreads();
+        const Hyp& h = sm.hyp;
+        const bool white_off = prm.chunk_mingap2[chunk] < h.thr;
+        // per-point vectors: phase of t_i / P reduced in double-double, diagonal noise, working copy of y
+        for (int i = tid; i < npad; i += NT) {
+            double s = 0.0, c = 1.0, dg = 0.0, yy = 0.0;
+            if (i < n) {
+                const double ti = t[i];
+                const double hi = ti / h.P;
+                const double lo = fma(-hi, h.P, ti) / h.P;      // t/P = hi + lo to ~106 bits
+                const double ph = (hi - rint(hi)) + lo;          // |ph| <= 0.5 (+ tiny): sin^2 is invariant to the dropped integer
+                sincospi(ph, &s, &c);
+                const double e = sqrt(h.S + yerr[i] * yerr[i]);  // gprot/model.py:345-346
+                dg = e * e;
+                yy = y[i];
+            }
+            vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
+        }
+        __syncthreads();
+
+        double logdet = 0.0;     // sum log diag(L), meaningful in thread 0
+        double acc[4][4][2];
+        bool failed = false;
+
+        for (int J = 0; J < T && !failed; J++) {
+            const double* jrow = lbase + (size_t)(J * (J - 1) / 2) * BLKD;   // blocks (J, 0..J-1), contiguous
+            const int niter = 8 * J;
+            // ================= diagonal block (J, J)
+            {
+                const bool active = wr >= wc;
+                if (tid == 0) prologue<true>(sm, it, jrow, jrow, niter);
+                if (active) synth_tile<EXACT, true>(acc, J * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, white_off, lane);
+                accumulate<true>(sm, acc, it, jrow, jrow, niter, wr, wc, lane, active);
+                __syncthreads();                                   // all stages consumed: regionA becomes M
+                {
+                    double* M = sm.regionA;
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) {
+                            const int r = 32 * wr + 8 * mi + g, c = 32 * wc + 8 * ni + 2 * q;
+                            double2 v;
+                            v.x = (active && r >= c) ? -acc[mi][ni][0] : 0.0;
+                            v.y = (active && r >= c + 1) ? -acc[mi][ni][1] : 0.0;
+                            *reinterpret_cast<double2*>(M + r * LDM + c) = v;
+                        }
+                    if (tid < BS) sm.yj[tid] = yw[J * BS + tid];
+                }
+                __syncthreads();
+                diag_factor(sm, warp, lane, logdet);               // ends with __syncthreads
+                if (sm.fail) { failed = true; break; }
+                // W -> B-operand fragments (zeros above the diagonal of each 16 x 16 corner), z_J = W ytilde_J
+                {
+                    const double* M = sm.regionA;
+                    for (int s = 0; s < 8; s++) {
+                        const int cnt = (16 - 2 * s) * 128;
+                        double* dst = sm.W + w_slab_off(s);
+                        for (int d = tid; d < cnt; d += NT) {
+                            const int rgrel = d >> 7, kp = (d >> 6) & 1, ln = (d >> 1) & 31, hh = d & 1;
+                            const int c = 8 * (2 * s + rgrel) + (ln >> 2);
+                            const int m = 16 * s + 4 * (2 * kp + hh) + (ln & 3);
+                            dst[d] = (m < c) ? M[m * LDM + c] : ((m == c) ? sm.dinv[c] : 0.0);
+                        }
+                    }
+                    if (tid < BS) {
+                        const int r = tid;
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                        int m = 0;
+                        for (; m + 3 < r; m += 4) {
+                            s0 = fma(M[(m + 0) * LDM + r], sm.yj[m + 0], s0);
+                            s1 = fma(M[(m + 1) * LDM + r], sm.yj[m + 1], s1);
+                            s2 = fma(M[(m + 2) * LDM + r], sm.yj[m + 2], s2);
+                            s3 = fma(M[(m + 3) * LDM + r], sm.yj[m + 3], s3);
+                        }
+                        for (; m < r; m++) s0 = fma(M[m * LDM + r], sm.yj[m], s0);
+                        const double z = ((s0 + s1) + (s2 + s3)) + sm.dinv[r] * sm.yj[r];
+                        sm.zs[r] = z;
+                        double z2 = z * z;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+                        if (lane == 0) atomicAdd(&sm.quad, z2);
+                    }
+                }
+                fence_async();
+                __syncthreads();
+            }
+            // ================= blocks below the diagonal
+            for (int I = J + 1; I < T; I++) {
+                const double* irow = lbase + (size_t)(I * (I - 1) / 2) * BLKD;
+                if (tid == 0) prologue<false>(sm, it, irow, jrow, niter);
+                if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, white_off, lane);
+                else                                synth_tile<EXACT, true>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, white_off, lane);
+                accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, true);
+                __syncthreads();                                   // stages drained: regionA becomes the S_IJ staging block
+                store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc
+                __syncthreads();
+                // ---- L_IJ = S W^T : k runs over m <= c
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+                for (int s = 0; s < 2 * wc; s++) {
+                    const double* As = sm.regionA + s * SLAB;
+                    const double* Bs = sm.W + w_slab_off(s) - (2 * s) * 128;
+#pragma unroll
+                    for (int kp = 0; kp < 2; kp++) {
+                        double2 a[4], b[4];
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+                    }
+                }
+#pragma unroll
+                for (int ds = 0; ds < 2; ds++) {                   // the two slabs that cross the diagonal of W
+                    const int s = 2 * wc + ds;
+                    const double* As = sm.regionA + s * SLAB;
+                    const double* Bs = sm.W + w_slab_off(s) - (2 * s) * 128;
+#pragma unroll
+                    for (int kp = 0; kp < 2; kp++) {
+                        double2 a[4], b[4];
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++)
+                            if (4 * ds + 2 * kp <= 2 * ni + 1) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                        for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+                            for (int ni = 0; ni < 4; ni++)
+                                if (4 * ds + 2 * kp + hh <= 2 * ni + 1) {
+#pragma unroll
+                                    for (int mi = 0; mi < 4; mi++)
+                                        dmma(acc[mi][ni][0], acc[mi][ni][1], hh ? a[mi].y : a[mi].x, hh ? b[ni].y : b[ni].x);
+                                }
+                    }
+                }
+                // ---- ytilde_I -= L_IJ z_J (partials per warp column), store L_IJ
+                {
+                    double part[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) {
+                        const double z0 = sm.zs[32 * wc + 8 * ni + 2 * q], z1 = sm.zs[32 * wc + 8 * ni + 2 * q + 1];
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++) part[mi] = fma(acc[mi][ni][0], z0, fma(acc[mi][ni][1], z1, part[mi]));
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++) {
+                        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 1);
+                        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 2);
+                        if (q == 0) sm.red[wc * BS + 32 * wr + 8 * mi + g] = part[mi];
+                    }
+                }
+                __syncthreads();                                   // staging reads done, partials visible
+                store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
+                if (tid < BS) {
+                    const int r = tid;
+                    yw[I * BS + r] -= (sm.red[r] + sm.red[BS + r]) + (sm.red[2 * BS + r] + sm.red[3 * BS + r]);
+                }
+                __threadfence();
+                fence_async();
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
+            double lnl;
+            if (failed) lnl = -INFINITY;
+            else {
+                lnl = -0.5 * sm.quad - 0.5 * (2.0 * logdet + (double)n * 1.8378770664093453);   // log(2 pi)
+                if (!(fabs(lnl) <= DBL_MAX)) lnl = -INFINITY;                                   // gprot/model.py:356
+            }
+            prm.prob_out[prob] = lnl;
+        }
+    }
+}
+
+// out[b] = sum over the row's problems, in a fixed order (gprot/model.py:362-365 np.sum over chunks)
+__global__ void reduce_rows_kernel(const double* __restrict__ prob_out, const int* __restrict__ row_first,
+                                   const int* __restrict__ row_count, double* __restrict__ out, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int f = row_first[b], c = row_count[b];
+    double s;
+    if (c <= 0) s = -INFINITY;
+    else {
+        s = 0.0;
+        for (int i = 0; i < c; i++) s += prob_out[f + i];
+        if (!(fabs(s) <= DBL_MAX)) s = -INFINITY;
+    }
+    out[b] = s;
+}
+
+// register-resident DMMA loop: the roofline denominator (same loop as tools/microbench.cu k_dmma<8>)
+__global__ void dmma_peak_kernel(double* out, int iters, long long* cyc) {
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { acc[i][0] = threadIdx.x * 1e-9; acc[i][1] = i; }
+    const double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+    const long long t0 = clock64();
+    for (int k = 0; k < iters; k++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) dmma(acc[i][0], acc[i][1], a, b);
+    }
+    const long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i][0] + acc[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+}  // namespace gprot

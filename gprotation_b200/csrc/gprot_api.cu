@@ -1,0 +1,453 @@
+// gprot_api.cu -- C ABI (include/gprot_b200.h) over the sm_100a kernels in gp_kernel.cuh.
+// Host side of the boundary: light-curve arena, problem queue, work-slot scratch, launches.
+// No CPU fallback: every numeric result comes from gp_lnlike_kernel.
+#include "../../include/gprot_b200.h"
+#include "gp_kernel.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace gprot;
+
+struct gprot_ctx {
+    int device = 0;
+    int num_sms = 0;
+    std::string err;
+    // host copy of the arena
+    std::vector<double> h_t, h_y, h_yerr;
+    std::vector<long long> h_chunk_off;
+    std::vector<int> h_chunk_n;
+    std::vector<double> h_chunk_mingap2;
+    std::vector<int> lc_first_chunk, lc_nchunks;
+    bool arena_dirty = true;
+    // device copies
+    double *d_t = nullptr, *d_y = nullptr, *d_yerr = nullptr, *d_chunk_mingap2 = nullptr;
+    long long* d_chunk_off = nullptr;
+    int* d_chunk_n = nullptr;
+    // per-call buffers (grown on demand)
+    double* d_theta = nullptr; size_t cap_theta = 0;
+    double* d_out = nullptr; size_t cap_out = 0;
+    int *d_prob_theta = nullptr, *d_prob_chunk = nullptr; size_t cap_prob = 0;
+    double* d_prob_out = nullptr;
+    int *d_row_first = nullptr, *d_row_count = nullptr; size_t cap_rows = 0;
+    int* d_counter = nullptr;
+    // work-slot scratch
+    double* d_lscratch = nullptr; size_t lslot_stride = 0; int lslots = 0;
+    double* d_vscratch = nullptr; int v_npad = 0; int vslots = 0;
+    // problem-list cache (same B, all rows on one light curve, no mask)
+    long long cache_B = -1; int cache_lc = -1; int cache_nprob = 0; int cache_tmax = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int64_t launches = 0;
+    bool attr_set = false;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(gprot_ctx* ctx, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_err = msg;
+    return 1;
+}
+#define CU(ctx, call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+template <class T>
+int grow(gprot_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) CU(ctx, cudaFree(*p));
+    *p = nullptr;
+    size_t c = std::max(need, *cap * 2);
+    CU(ctx, cudaMalloc((void**)p, c * sizeof(T)));
+    *cap = c;
+    return 0;
+}
+
+int upload_arena(gprot_ctx* ctx) {
+    if (!ctx->arena_dirty) return 0;
+    CU(ctx, cudaDeviceSynchronize());
+    auto rea = [&](void** p, const void* src, size_t bytes) -> int {
+        if (*p) CU(ctx, cudaFree(*p));
+        *p = nullptr;
+        CU(ctx, cudaMalloc(p, std::max<size_t>(bytes, 16)));
+        CU(ctx, cudaMemcpy(*p, src, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    };
+    const size_t n = ctx->h_t.size(), m = ctx->h_chunk_n.size();
+    if (rea((void**)&ctx->d_t, ctx->h_t.data(), n * 8)) return 1;
+    if (rea((void**)&ctx->d_y, ctx->h_y.data(), n * 8)) return 1;
+    if (rea((void**)&ctx->d_yerr, ctx->h_yerr.data(), n * 8)) return 1;
+    if (rea((void**)&ctx->d_chunk_off, ctx->h_chunk_off.data(), m * 8)) return 1;
+    if (rea((void**)&ctx->d_chunk_n, ctx->h_chunk_n.data(), m * 4)) return 1;
+    if (rea((void**)&ctx->d_chunk_mingap2, ctx->h_chunk_mingap2.data(), m * 8)) return 1;
+    ctx->arena_dirty = false;
+    ctx->cache_B = -1;
+    return 0;
+}
+
+// gprot/model.py:22-23
+inline double ln_gauss(double x, double mu, double sigma) {
+    return -0.5 * ((x - mu) * (x - mu) / (sigma * sigma)) + std::log(1.0 / std::sqrt(2.0 * M_PI * sigma * sigma));
+}
+
+// gprot/model.py:132-163
+double lnprior_one(const double* th, const double* bounds, const double* mu, const double* sigma, double pmin,
+                   double pmax, const double* mix, int k) {
+    const double ninf = -std::numeric_limits<double>::infinity();
+    for (int i = 0; i < 5; i++)
+        if (th[i] < bounds[2 * i] || th[i] > bounds[2 * i + 1] || std::isnan(th[i])) return ninf;
+    if (th[4] < pmin || th[4] > pmax) return ninf;
+    if (th[1] < th[4]) return ninf;
+    double lnpr = 0.0;
+    for (int i = 0; i < 4; i++) lnpr += ln_gauss(th[i], mu[i], sigma[i]);
+    if (mix && k > 0) {   // logsumexp(lnGauss(p, mu_j, sigma_j), b=w_j), gprot/model.py:25-29
+        double mx = ninf;
+        std::vector<double> a(k);
+        for (int j = 0; j < k; j++) {
+            a[j] = ln_gauss(th[4], mix[3 * j + 1], mix[3 * j + 2]);
+            mx = std::max(mx, a[j]);
+        }
+        if (!std::isfinite(mx)) mx = 0.0;
+        double s = 0.0;
+        for (int j = 0; j < k; j++) s += mix[3 * j] * std::exp(a[j] - mx);
+        lnpr += std::log(s) + mx;
+    }
+    return lnpr;
+}
+
+// core: likelihood of the rows of theta selected by mask (NULL = all)
+int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* lc_id, const unsigned char* mask,
+                double* out, unsigned flags, cudaStream_t st) {
+    if (!ctx) return fail(nullptr, "null context");
+    if (B < 0 || (B > 0 && (!theta || !out))) return fail(ctx, "bad arguments");
+    if (B == 0) return 0;
+    if (ctx->lc_first_chunk.empty()) return fail(ctx, "no light curve registered");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (upload_arena(ctx)) return 1;
+
+    // ---- problem list
+    const bool cacheable = (lc_id == nullptr && mask == nullptr);
+    int nprob = 0, tmax = 0;
+    if (cacheable && ctx->cache_B == B && ctx->cache_lc == 0) {
+        nprob = ctx->cache_nprob;
+        tmax = ctx->cache_tmax;
+    } else {
+        std::vector<int> ptheta, pchunk, rfirst((size_t)B), rcount((size_t)B);
+        const int nlc = (int)ctx->lc_first_chunk.size();
+        for (int64_t b = 0; b < B; b++) {
+            const int lc = lc_id ? lc_id[b] : 0;
+            if (lc < 0 || lc >= nlc) return fail(ctx, "lc_id out of range");
+            rfirst[b] = (int)ptheta.size();
+            if (mask && !mask[b]) { rcount[b] = 0; continue; }
+            const int f = ctx->lc_first_chunk[lc], m = ctx->lc_nchunks[lc];
+            rcount[b] = m;
+            for (int c = 0; c < m; c++) {
+                ptheta.push_back((int)b);
+                pchunk.push_back(f + c);
+                tmax = std::max(tmax, (ctx->h_chunk_n[f + c] + BS - 1) / BS);
+            }
+        }
+        nprob = (int)ptheta.size();
+        if ((size_t)B > ctx->cap_rows) {
+            if (ctx->d_row_first) cudaFree(ctx->d_row_first);
+            if (ctx->d_row_count) cudaFree(ctx->d_row_count);
+            ctx->d_row_first = ctx->d_row_count = nullptr;
+            const size_t c = std::max<size_t>((size_t)B, ctx->cap_rows * 2);
+            CU(ctx, cudaMalloc((void**)&ctx->d_row_first, c * 4));
+            CU(ctx, cudaMalloc((void**)&ctx->d_row_count, c * 4));
+            ctx->cap_rows = c;
+        }
+        if ((size_t)nprob > ctx->cap_prob) {
+            if (ctx->d_prob_theta) cudaFree(ctx->d_prob_theta);
+            if (ctx->d_prob_chunk) cudaFree(ctx->d_prob_chunk);
+            if (ctx->d_prob_out) cudaFree(ctx->d_prob_out);
+            ctx->d_prob_theta = ctx->d_prob_chunk = nullptr; ctx->d_prob_out = nullptr;
+            const size_t c = std::max<size_t>(nprob, ctx->cap_prob * 2);
+            CU(ctx, cudaMalloc((void**)&ctx->d_prob_theta, c * 4));
+            CU(ctx, cudaMalloc((void**)&ctx->d_prob_chunk, c * 4));
+            CU(ctx, cudaMalloc((void**)&ctx->d_prob_out, c * 8));
+            ctx->cap_prob = c;
+        }
+        CU(ctx, cudaMemcpyAsync(ctx->d_row_first, rfirst.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaMemcpyAsync(ctx->d_row_count, rcount.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+        if (nprob > 0) {
+            CU(ctx, cudaMemcpyAsync(ctx->d_prob_theta, ptheta.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
+            CU(ctx, cudaMemcpyAsync(ctx->d_prob_chunk, pchunk.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
+        }
+        CU(ctx, cudaStreamSynchronize(st));   // the host vectors go out of scope
+        if (cacheable) { ctx->cache_B = B; ctx->cache_lc = 0; ctx->cache_nprob = nprob; ctx->cache_tmax = tmax; }
+        else ctx->cache_B = -1;
+    }
+
+    // ---- theta / out on the device
+    const double* d_theta = theta;
+    if (!(flags & GPROT_THETA_ON_DEVICE)) {
+        if (grow(ctx, &ctx->d_theta, &ctx->cap_theta, (size_t)B * 5)) return 1;
+        CU(ctx, cudaMemcpyAsync(ctx->d_theta, theta, (size_t)B * 40, cudaMemcpyHostToDevice, st));
+        d_theta = ctx->d_theta;
+    }
+    double* d_out = out;
+    if (!(flags & GPROT_OUT_ON_DEVICE)) {
+        if (grow(ctx, &ctx->d_out, &ctx->cap_out, (size_t)B)) return 1;
+        d_out = ctx->d_out;
+    }
+
+    if (nprob > 0) {
+        // ---- work slots: one persistent CTA per SM, each with its own factor scratch
+        int slots = std::min(nprob, ctx->num_sms);
+        const size_t stride = std::max<size_t>((size_t)tmax * (tmax - 1) / 2, 1) * BLKD;
+        const int npad = tmax * BS;
+        if (stride > ctx->lslot_stride || slots > ctx->lslots) {
+            CU(ctx, cudaDeviceSynchronize());
+            if (ctx->d_lscratch) CU(ctx, cudaFree(ctx->d_lscratch));
+            ctx->d_lscratch = nullptr;
+            const size_t s2 = std::max(stride, ctx->lslot_stride);
+            int want = std::max(slots, ctx->lslots);
+            size_t freeb = 0, totalb = 0;
+            CU(ctx, cudaMemGetInfo(&freeb, &totalb));
+            const size_t budget = (size_t)(0.85 * (double)freeb);
+            while (want > 1 && (size_t)want * s2 * 8 > budget) want--;
+            if ((size_t)want * s2 * 8 > budget) return fail(ctx, "not enough device memory for one factor scratch slot");
+            CU(ctx, cudaMalloc((void**)&ctx->d_lscratch, (size_t)want * s2 * 8));
+            ctx->lslot_stride = s2;
+            ctx->lslots = want;
+        }
+        slots = std::min(slots, ctx->lslots);
+        if (npad > ctx->v_npad || slots > ctx->vslots) {
+            CU(ctx, cudaDeviceSynchronize());
+            if (ctx->d_vscratch) CU(ctx, cudaFree(ctx->d_vscratch));
+            ctx->d_vscratch = nullptr;
+            const int np2 = std::max(npad, ctx->v_npad);
+            const int want = std::max(ctx->lslots, ctx->vslots);
+            CU(ctx, cudaMalloc((void**)&ctx->d_vscratch, (size_t)want * 4 * np2 * 8));
+            ctx->v_npad = np2;
+            ctx->vslots = want;
+        }
+        if (!ctx->attr_set) {
+            CU(ctx, cudaFuncSetAttribute(gp_lnlike_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+            CU(ctx, cudaFuncSetAttribute(gp_lnlike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+            ctx->attr_set = true;
+        }
+        Params prm;
+        prm.t = ctx->d_t; prm.y = ctx->d_y; prm.yerr = ctx->d_yerr;
+        prm.chunk_off = ctx->d_chunk_off; prm.chunk_n = ctx->d_chunk_n; prm.chunk_mingap2 = ctx->d_chunk_mingap2;
+        prm.theta = d_theta;
+        prm.prob_theta = ctx->d_prob_theta; prm.prob_chunk = ctx->d_prob_chunk; prm.prob_out = ctx->d_prob_out;
+        prm.nprob = nprob;
+        prm.counter = ctx->d_counter;
+        prm.lscratch = ctx->d_lscratch; prm.lslot_stride = ctx->lslot_stride;
+        prm.vscratch = ctx->d_vscratch; prm.npad_max = ctx->v_npad;
+        CU(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
+        CU(ctx, cudaEventRecord(ctx->ev0, st));
+        if (flags & GPROT_EXACT_KERNEL) gp_lnlike_kernel<true><<<slots, NT, sizeof(Smem), st>>>(prm);
+        else                            gp_lnlike_kernel<false><<<slots, NT, sizeof(Smem), st>>>(prm);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(ctx->ev1, st));
+        ctx->launches++;
+    }
+    reduce_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(ctx->d_prob_out, ctx->d_row_first, ctx->d_row_count, d_out, (long long)B);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (!(flags & GPROT_OUT_ON_DEVICE)) {
+        CU(ctx, cudaMemcpyAsync(out, d_out, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        if (nprob > 0) CU(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gprot_abi_version(void) { return 1; }
+
+const char* gprot_last_error(const gprot_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int gprot_create(int device, gprot_ctx** out) {
+    if (!out) return fail(nullptr, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, std::string("no CUDA device: gprot_b200 has no CPU fallback (") + cudaGetErrorString(e) + ")");
+    if (device < 0 || device >= ndev) return fail(nullptr, "device ordinal out of range");
+    gprot_ctx* ctx = new (std::nothrow) gprot_ctx;
+    if (!ctx) return fail(nullptr, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp p;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&p, device) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, "cudaSetDevice / cudaGetDeviceProperties failed");
+    }
+    if (p.major != 10) {
+        delete ctx;
+        return fail(nullptr, "gprot_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(p.major) + std::to_string(p.minor));
+    }
+    ctx->num_sms = p.multiProcessorCount;
+    if (cudaMalloc((void**)&ctx->d_counter, 64) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, "context allocation failed");
+    }
+    *out = ctx;
+    return 0;
+}
+
+int gprot_destroy(gprot_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {ctx->d_t, ctx->d_y, ctx->d_yerr, ctx->d_chunk_mingap2, ctx->d_chunk_off, ctx->d_chunk_n, ctx->d_theta,
+                    ctx->d_out, ctx->d_prob_theta, ctx->d_prob_chunk, ctx->d_prob_out, ctx->d_row_first, ctx->d_row_count,
+                    ctx->d_counter, ctx->d_lscratch, ctx->d_vscratch};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    delete ctx;
+    return 0;
+}
+
+int gprot_register_lc(gprot_ctx* ctx, int m, const int* n, const double* t, const double* y, const double* yerr, int* lc_id) {
+    if (!ctx) return fail(nullptr, "null context");
+    if (m <= 0 || !n || !t || !y || !yerr) return fail(ctx, "bad arguments");
+    size_t pos = 0;
+    for (int c = 0; c < m; c++) {
+        if (n[c] <= 0) return fail(ctx, "empty chunk");
+        pos += (size_t)n[c];
+    }
+    const int first = (int)ctx->h_chunk_n.size();
+    pos = 0;
+    for (int c = 0; c < m; c++) {
+        ctx->h_chunk_off.push_back((long long)ctx->h_t.size());
+        ctx->h_chunk_n.push_back(n[c]);
+        std::vector<double> s(t + pos, t + pos + n[c]);
+        std::sort(s.begin(), s.end());
+        double g2 = std::numeric_limits<double>::infinity();
+        for (int i = 1; i < n[c]; i++) {
+            const double d = s[i] - s[i - 1];
+            g2 = std::min(g2, d * d);
+        }
+        ctx->h_chunk_mingap2.push_back(g2);
+        ctx->h_t.insert(ctx->h_t.end(), t + pos, t + pos + n[c]);
+        ctx->h_y.insert(ctx->h_y.end(), y + pos, y + pos + n[c]);
+        ctx->h_yerr.insert(ctx->h_yerr.end(), yerr + pos, yerr + pos + n[c]);
+        // keep every chunk 16-byte aligned in the arena
+        if (ctx->h_t.size() & 1) { ctx->h_t.push_back(0.0); ctx->h_y.push_back(0.0); ctx->h_yerr.push_back(0.0); }
+        pos += (size_t)n[c];
+    }
+    ctx->lc_first_chunk.push_back(first);
+    ctx->lc_nchunks.push_back(m);
+    ctx->arena_dirty = true;
+    if (lc_id) *lc_id = (int)ctx->lc_first_chunk.size() - 1;
+    return 0;
+}
+
+int gprot_unregister_all(gprot_ctx* ctx) {
+    if (!ctx) return fail(nullptr, "null context");
+    ctx->h_t.clear(); ctx->h_y.clear(); ctx->h_yerr.clear();
+    ctx->h_chunk_off.clear(); ctx->h_chunk_n.clear(); ctx->h_chunk_mingap2.clear();
+    ctx->lc_first_chunk.clear(); ctx->lc_nchunks.clear();
+    ctx->arena_dirty = true;
+    ctx->cache_B = -1;
+    return 0;
+}
+
+int gprot_lnlike_batch(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* lc_id, double* out, unsigned flags,
+                       void* stream) {
+    return lnlike_core(ctx, B, theta, lc_id, nullptr, out, flags, (cudaStream_t)stream);
+}
+
+int gprot_lnprior_batch(int64_t B, const double* theta, const double* bounds, const double* mu, const double* sigma,
+                        double pmin, double pmax, const double* mixture, int k, double* out) {
+    if (B < 0 || (B > 0 && (!theta || !bounds || !mu || !sigma || !out))) return fail(nullptr, "bad arguments");
+    for (int64_t b = 0; b < B; b++) out[b] = lnprior_one(theta + 5 * b, bounds, mu, sigma, pmin, pmax, mixture, k);
+    return 0;
+}
+
+int gprot_lnpost_batch(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* lc_id, const double* bounds,
+                       const double* mu, const double* sigma, double pmin, double pmax, const double* mixture, int k,
+                       double* out_lnprior, double* out_lnlike, unsigned flags, void* stream) {
+    if (!ctx) return fail(nullptr, "null context");
+    if (flags & (GPROT_THETA_ON_DEVICE | GPROT_OUT_ON_DEVICE)) return fail(ctx, "gprot_lnpost_batch takes host buffers");
+    if (B > 0 && (!out_lnprior || !out_lnlike)) return fail(ctx, "bad arguments");
+    if (gprot_lnprior_batch(B, theta, bounds, mu, sigma, pmin, pmax, mixture, k, out_lnprior)) return fail(ctx, g_err);
+    std::vector<unsigned char> mask((size_t)B);
+    for (int64_t b = 0; b < B; b++) mask[b] = std::isfinite(out_lnprior[b]) ? 1 : 0;
+    return lnlike_core(ctx, B, theta, lc_id, mask.data(), out_lnlike, flags, (cudaStream_t)stream);
+}
+
+int gprot_sync(gprot_ctx* ctx) {
+    if (!ctx) return fail(nullptr, "null context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    return 0;
+}
+
+int gprot_last_kernel_ms(gprot_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(ctx, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    CU(ctx, cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    *ms = ctx->last_ms;
+    return 0;
+}
+
+int64_t gprot_launch_count(const gprot_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gprot_measure_dmma_peak(gprot_ctx* ctx, double* tflops, double* sm_clock_mhz) {
+    if (!ctx || !tflops) return fail(ctx, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    double* out = nullptr;
+    long long* cyc = nullptr;
+    const int grid = ctx->num_sms, block = 512, iters = 40000;
+    CU(ctx, cudaMalloc((void**)&out, (size_t)grid * block * 8));
+    CU(ctx, cudaMalloc((void**)&cyc, 8));
+    cudaEvent_t e0, e1;
+    CU(ctx, cudaEventCreate(&e0));
+    CU(ctx, cudaEventCreate(&e1));
+    dmma_peak_kernel<<<grid, block>>>(out, iters, cyc);
+    CU(ctx, cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        CU(ctx, cudaEventRecord(e0));
+        dmma_peak_kernel<<<grid, block>>>(out, iters, cyc);
+        CU(ctx, cudaEventRecord(e1));
+        CU(ctx, cudaEventSynchronize(e1));
+        float ms;
+        CU(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    long long c = 0;
+    CU(ctx, cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
+    const double nmma = (double)grid * (block / 32) * (double)iters * 8.0;
+    *tflops = nmma * 512.0 / (best * 1e-3) / 1e12;
+    if (sm_clock_mhz) *sm_clock_mhz = (double)c / (best * 1e-3) / 1e6;
+    cudaFree(out); cudaFree(cyc); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->launches += 4;
+    return 0;
+}
+
+int gprot_debug_read_scratch(gprot_ctx* ctx, int slot, size_t offset, size_t count, double* host_out) {
+    if (!ctx || !host_out) return fail(ctx, "bad arguments");
+    if (!ctx->d_lscratch || slot < 0 || slot >= ctx->lslots || offset + count > ctx->lslot_stride) return fail(ctx, "scratch range");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemcpy(host_out, ctx->d_lscratch + (size_t)slot * ctx->lslot_stride + offset, count * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

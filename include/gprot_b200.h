@@ -1,0 +1,95 @@
+/* gprot_b200.h -- C ABI of the B200-native quasi-periodic GP log-likelihood engine.
+ *
+ * This is the drop-in boundary for ONE path of RuthAngus/GProtation: the likelihood that
+ * emcee3 evaluates for every walker proposal.  Each entry point cites the reference
+ * interface it replaces (paths relative to the reference repository root).  The reference
+ * is pure Python on top of george; the binding a maintainer adds is the ctypes stub shown
+ * in INTEGRATION.md (gprotation_b200/_lib.py is that stub, shipped).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - every function returns 0 on success, non-zero on argument/CUDA errors
+ *     (text via gprot_last_error); NUMERICAL failure is data: the affected output is -inf,
+ *     exactly like gprot/model.py:349-356 maps LinAlgError / non-finite values to -inf;
+ *   - theta rows are (ln A, ln l, ln G, ln sigma, ln P), natural logs (gprot/model.py:42);
+ *   - a context is bound to one CUDA device, calls on one context are stream-ordered and
+ *     not re-entrant (SURVEY.md section 8b "Threading").
+ *   - there is NO CPU fallback: without a CUDA device gprot_create fails.
+ */
+#ifndef GPROT_B200_H
+#define GPROT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gprot_ctx gprot_ctx;
+
+/* flags for gprot_lnlike_batch */
+#define GPROT_THETA_ON_DEVICE 1u /* theta points to device memory                         */
+#define GPROT_OUT_ON_DEVICE   2u /* out points to device memory (no D2H, no sync)         */
+#define GPROT_EXACT_KERNEL    4u /* evaluate every covariance entry in george's operation
+                                    order (sin(M_PI*d/P), two exps, divisions) instead of
+                                    the fast per-point-phase form; ~3x slower synthesis   */
+
+/* ABI / build identification. */
+int gprot_abi_version(void);
+
+/* Replaces the per-process george/solver state that each schwimmbad worker holds
+ * (scripts/gprot-fit:195, gprot/fit.py:94-98).  device = CUDA ordinal. */
+int gprot_create(int device, gprot_ctx **ctx);
+int gprot_destroy(gprot_ctx *ctx);
+const char *gprot_last_error(const gprot_ctx *ctx);
+
+/* Registers one light curve made of m chunks (m = 1: the --nochunks single N x N problem;
+ * m > 1: lc.x_list / y_list / yerr_list of gprot/lc.py:329-342, 375-391).  n[m] are the chunk
+ * lengths; t, y, yerr hold the chunks back to back (sum(n) doubles each, host memory).
+ * The arrays are copied to the device once (the reference re-sends them to george.GP.compute on
+ * every call, gprot/model.py:343-346).  Returns an id through lc_id. */
+int gprot_register_lc(gprot_ctx *ctx, int m, const int *n, const double *t, const double *y,
+                      const double *yerr, int *lc_id);
+int gprot_unregister_all(gprot_ctx *ctx);
+
+/* GPRotModel.lnlike(theta) for B proposals in ONE launch (gprot/model.py:358-365 called
+ * per walker from Emcee3Model.compute_log_likelihood, gprot/fit.py:20-22):
+ *   out[b] = sum over chunks c of lc_id[b] of lnlike_function(theta[b], x_c, y_c, yerr_c)
+ * theta is [B,5] row-major; lc_id is [B] (NULL: every row uses light curve 0);
+ * stream is a cudaStream_t cast to void* (NULL: the legacy default stream).
+ * Without GPROT_OUT_ON_DEVICE the call copies out to the host and synchronises. */
+int gprot_lnlike_batch(gprot_ctx *ctx, int64_t B, const double *theta, const int32_t *lc_id,
+                       double *out, unsigned flags, void *stream);
+
+/* GPRotModel.lnprior(theta) (gprot/model.py:132-163) for B rows, evaluated on the host side of
+ * the boundary (it is 20 flops): bounds[10] = (lo,hi) x 5, mu[4], sigma[4], mixture = k rows of
+ * (w, mu, sigma) or NULL when acf_prior is off. */
+int gprot_lnprior_batch(int64_t B, const double *theta, const double *bounds, const double *mu,
+                        const double *sigma, double pmin, double pmax, const double *mixture, int k,
+                        double *out);
+
+/* GPRotModel.lnpost(theta) = lnlike + lnprior (gprot/model.py:367-369) for B rows.  Rows whose
+ * prior is -inf are not factorised (emcee3 never asks for their likelihood); they return -inf. */
+int gprot_lnpost_batch(gprot_ctx *ctx, int64_t B, const double *theta, const int32_t *lc_id,
+                       const double *bounds, const double *mu, const double *sigma, double pmin,
+                       double pmax, const double *mixture, int k, double *out_lnprior,
+                       double *out_lnlike, unsigned flags, void *stream);
+
+int gprot_sync(gprot_ctx *ctx);
+
+/* Measurement hooks (bench.py): device time of the last likelihood launch, CUDA events on the
+ * launching stream; number of kernels launched by this context so far; FP64 tensor (DMMA) peak
+ * of this device measured by a register-resident mma.sync.m8n8k4.f64 loop. */
+int gprot_last_kernel_ms(gprot_ctx *ctx, float *ms);
+int64_t gprot_launch_count(const gprot_ctx *ctx);
+int gprot_measure_dmma_peak(gprot_ctx *ctx, double *tflops, double *sm_clock_mhz);
+
+/* Test hook: copy `count` doubles of work-slot `slot`'s factor scratch to the host
+ * (fragment-major 128 x 128 blocks, strictly-lower block rows). */
+int gprot_debug_read_scratch(gprot_ctx *ctx, int slot, size_t offset, size_t count, double *host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPROT_B200_H */
