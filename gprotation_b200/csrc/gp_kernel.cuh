@@ -50,7 +50,7 @@ struct Smem {
     double dinv[BS];              // 1 / diag(L_JJ)
     double wt[64];                // inverse of the current 8 x 8 diagonal tile
     Hyp hyp;
-    double quad;
+    double qpart[4];              // per-warp partial sums of z_J^2 (fixed-order reduction: deterministic)
     unsigned long long full[STAGES];
     unsigned long long empty[STAGES];
     int prob;
@@ -403,7 +403,6 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         if (tid == 0) {
             sm.prob = atomicAdd(prm.counter, 1);
             sm.fail = 0;
-            sm.quad = 0.0;
         }
         __syncthreads();
         const int prob = sm.prob;
@@ -446,7 +445,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         }
         __syncthreads();
 
-        double logdet = 0.0;     // sum log diag(L), meaningful in thread 0
+        double logdet = 0.0, quad = 0.0;     // sum log diag(L) and |z|^2, meaningful in thread 0
         double acc[4][4][2];
         bool failed = false;
 
@@ -506,11 +505,12 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                         double z2 = z * z;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) z2 += __shfl_xor_sync(0xffffffffu, z2, o);
-                        if (lane == 0) atomicAdd(&sm.quad, z2);
+                        if (lane == 0) sm.qpart[warp] = z2;
                     }
                 }
                 fence_async();
                 __syncthreads();
+                if (tid == 0) quad += (sm.qpart[0] + sm.qpart[1]) + (sm.qpart[2] + sm.qpart[3]);
             }
             // ================= blocks below the diagonal
             for (int I = J + 1; I < T; I++) {
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             double lnl;
             if (failed) lnl = -INFINITY;
             else {
-                lnl = -0.5 * sm.quad - 0.5 * (2.0 * logdet + (double)n * 1.8378770664093453);   // log(2 pi)
+                lnl = -0.5 * quad - 0.5 * (2.0 * logdet + (double)n * 1.8378770664093453);   // log(2 pi)
                 if (!(fabs(lnl) <= DBL_MAX)) lnl = -INFINITY;                                   // gprot/model.py:356
             }
             prm.prob_out[prob] = lnl;

@@ -36,8 +36,9 @@ DEFAULT_BOUNDS = ((-20.0, 0.0), (2.0, 20.0), (-10.0, 3.0), (-20.0, 0.0), (-0.69,
 DEFAULT_GP_PRIOR_MU = (-13.0, 7.2, -2.3, -17.0)
 DEFAULT_GP_PRIOR_SIGMA = (5.7, 1.2, 1.4, 5.0)
 # gprot/kepler.py:27-34 (KeplerGPRotModel overrides)
-KEPLER_BOUNDS = ((-20.0, 5.0), (2.0, 20.0), (-10.0, 3.0), (-20.0, 5.0), (-0.69, 4.61))
-KEPLER_GP_PRIOR_MU = (-5.0, 7.2, -2.3, -5.0)
+KEPLER_BOUNDS = ((-20.0, 0.0), (2.0, 8.0), (0.0, 3.0), (-20.0, 0.0), (-0.69, 4.61))
+KEPLER_GP_PRIOR_MU = (-13.0, 5.0, 1.9, -17.0)
+KEPLER_GP_PRIOR_SIGMA = (5.7, 1.2, 1.4, 5.0)
 
 
 def hyper(theta):

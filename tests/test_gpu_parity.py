@@ -1,0 +1,249 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (gprot_lnlike_batch / gprot_lnpost_batch).
+
+Tolerance (north star): |lnlike_gpu - lnlike_oracle| <= 1e-9 * |lnlike_oracle| in fp64 on prior-typical draws.
+Both sides are fp64 factorisations with different summation orders, so their difference grows like
+eps * cond(K); the bound is therefore written as  TOL(cond) = 1e-9 * max(1, cond / 1e7)  and every test
+asserts it with the condition number of the actual matrix (prior draws have cond ~1e2..1e6; the tail above
+1e7 is covered by the scaled bound and by comparison against the 80-bit long-double evaluation).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as o
+from gprotation_b200.synth import synthetic_lightcurve
+
+pytestmark = pytest.mark.gpu
+
+
+def tol(cond):
+    return 1e-9 * np.maximum(1.0, np.asarray(cond) / 1e7)
+
+
+def cond_of(th, t, yerr):
+    ev = np.linalg.eigvalsh(o.kernel_matrix(th, t, yerr))
+    return ev[-1] / ev[0]
+
+
+def check(got, ref, conds, what=""):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref)), what
+    m = np.isfinite(ref)
+    rel = np.abs(got[m] - ref[m]) / np.abs(ref[m])
+    assert np.all(rel <= tol(np.asarray(conds)[m])), (what, rel, tol(np.asarray(conds)[m]))
+    return rel
+
+
+@pytest.mark.parametrize("name", ["n24", "n64", "n150", "n300c100", "n257"])
+@pytest.mark.parametrize("exact", [False, True])
+def test_golden_fixtures(engine, golden, name, exact):
+    t, y, yerr = golden[name + "_t"], golden[name + "_y"], golden[name + "_yerr"]
+    cs = int(golden[name + "_chunksize"])
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr, chunks=o.split_chunks(len(t), None if cs < 0 else cs))
+    got = engine.lnlike_batch(golden[name + "_theta"], lc_id=lc, exact=exact)
+    check(got, golden[name + "_lnlike"], golden[name + "_cond"], name)
+    # and against the long-double evaluation: the GPU is no further from the truth than fp64 rounding allows
+    ld = golden[name + "_lnlike_c_ld"]
+    assert np.all(np.abs(got - ld) <= 1e-13 * np.maximum(1e4, golden[name + "_cond"]) * np.abs(ld))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 127, 128, 129, 255, 256, 300, 385, 1000])
+def test_sizes_and_padding_edges(engine, n):
+    t, y, yerr, truth = synthetic_lightcurve(n, n, baseline=max(50.0, 0.7 * n))
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    th = o.sample_from_prior(6, seed=n)
+    th[0] = truth
+    ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th])
+    conds = [cond_of(x, t, yerr) for x in th]
+    for exact in (False, True):
+        check(engine.lnlike_batch(th, lc_id=lc, exact=exact), ref, conds, "n=%d exact=%d" % (n, exact))
+
+
+def test_analytic_n1_n2(engine):
+    engine.unregister_all()
+    th = np.array([[-3.0, 5.0, -1.0, -4.0, 1.0]])
+    A, L, G, S, P = np.exp(th[0])
+    a = engine.register_lc([3.7], [0.3], [0.05])
+    k = A + 2 * S + 0.05 ** 2
+    want = -0.5 * (0.3 ** 2 / k + math.log(k) + math.log(2 * math.pi))
+    assert abs(engine.lnlike_batch(th, lc_id=a)[0] - want) <= 1e-13 * abs(want)
+    b = engine.register_lc([0.0, 1.3], [0.2, -0.4], [0.01, 0.02])
+    d = 1.3
+    k01 = A * math.exp(-d * d / (2 * L)) * math.exp(-G * math.sin(math.pi * d / P) ** 2)
+    k00, k11 = A + 2 * S + 0.01 ** 2, A + 2 * S + 0.02 ** 2
+    det = k00 * k11 - k01 ** 2
+    quad = (k11 * 0.04 + 2 * k01 * 0.08 + k00 * 0.16) / det
+    want = -0.5 * (quad + math.log(det) + 2 * math.log(2 * math.pi))
+    assert abs(engine.lnlike_batch(th, lc_id=b)[0] - want) <= 1e-12 * abs(want)
+
+
+def test_chunked_equals_sum_of_chunks_and_ragged_batch(engine):
+    """Several light curves of different lengths and chunkings in ONE launch, rows interleaved."""
+    engine.unregister_all()
+    lcs = []
+    for s, (n, cs) in enumerate([(700, 300), (300, None), (1000, 200), (130, 64), (5, 2)]):
+        t, y, yerr, _ = synthetic_lightcurve(40 + s, n, baseline=800.0)
+        chunks = o.split_chunks(n, cs)
+        lcs.append((engine.register_lc(t, y, yerr, chunks=chunks), t, y, yerr, chunks))
+    th = o.sample_from_prior(20, seed=77)
+    ids = np.arange(20) % len(lcs)
+    got = engine.lnlike_batch(th, lc_id=ids)
+    ref, conds = [], []
+    for x, i in zip(th, ids):
+        _, t, y, yerr, chunks = lcs[i]
+        ref.append(o.lnlike(x, t, y, yerr, chunks))
+        parts = chunks if chunks is not None else [np.arange(len(t))]
+        conds.append(max(cond_of(x, t[c], yerr[c]) for c in parts))
+    check(got, ref, conds, "ragged")
+    # LightCurve.x_list route gives the same numbers as explicit index chunks
+    from gprotation_b200.lc import LightCurve
+
+    _, t, y, yerr, chunks = lcs[0]
+    lcobj = LightCurve(t, y, yerr, chunksize=300)
+    lid = engine.register_lc_arrays(lcobj.x_list, lcobj.y_list, lcobj.yerr_list)
+    assert np.array_equal(engine.lnlike_batch(th[:4], lc_id=lid), engine.lnlike_batch(th[:4], lc_id=lcs[0][0]))
+
+
+def test_failure_rows_are_minus_inf_and_do_not_poison_the_batch(engine):
+    t, y, yerr, _ = synthetic_lightcurve(3, 200, baseline=300.0)
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    th = o.sample_from_prior(6, seed=5)
+    ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th])
+    bad = th.copy()
+    bad[1, 0] = np.nan
+    bad[3, 4] = np.nan
+    bad[4, 0] = 800.0                      # exp overflows: K = inf
+    got = engine.lnlike_batch(bad, lc_id=lc)
+    assert got[1] == -np.inf and got[3] == -np.inf and got[4] == -np.inf
+    assert not np.any(np.isnan(got))
+    good = [0, 2, 5]
+    check(got[good], ref[good], [cond_of(th[i], t, yerr) for i in good])
+
+
+def test_coincident_time_stamps_fire_the_white_kernel_off_diagonal(engine):
+    """george's WhiteKernel adds S wherever r2 < DBL_EPSILON, i.e. also between duplicated stamps."""
+    t, y, yerr, _ = synthetic_lightcurve(8, 160, baseline=300.0)
+    t = t.copy()
+    t[17] = t[16]
+    t[140] = t[3]                          # a duplicate in another 128-block
+    yerr = np.full_like(t, 1e-3)
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    th = o.sample_from_prior(4, seed=8)
+    th[:, 3] = -9.0                        # make S matter
+    ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th])
+    conds = [cond_of(x, t, yerr) for x in th]
+    for exact in (False, True):
+        check(engine.lnlike_batch(th, lc_id=lc, exact=exact), ref, conds, "dups")
+
+
+def test_unsorted_input_and_scaling_property_full_size(engine):
+    """Size-independent properties at the BASELINE size N=2048: permutation invariance and
+    y->cy, A->c^2 A, S->c^2 S, yerr->c yerr  =>  lnlike -> lnlike - N ln c."""
+    n = 2048
+    t, y, yerr, truth = synthetic_lightcurve(1, n, kind="harmonic")
+    th = o.sample_from_prior(8, seed=21)
+    p = np.random.default_rng(0).permutation(n)
+    c = 2.5
+    th2 = th.copy()
+    th2[:, 0] += 2 * math.log(c)
+    th2[:, 3] += 2 * math.log(c)
+    engine.unregister_all()
+    a = engine.register_lc(t, y, yerr)
+    b = engine.register_lc(t[p], y[p], yerr[p])
+    s = engine.register_lc(t, c * y, c * yerr)
+    base = engine.lnlike_batch(th, lc_id=a)
+    perm = engine.lnlike_batch(th, lc_id=b)
+    scal = engine.lnlike_batch(th2, lc_id=s)
+    ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th[:4]])
+    conds = np.array([cond_of(x, t, yerr) for x in th])
+    check(base[:4], ref, conds[:4], "n2048 vs oracle")
+    assert np.all(np.abs(perm - base) <= 10 * tol(conds) * np.abs(base))
+    assert np.all(np.abs(scal - (base - n * math.log(c))) <= 10 * tol(conds) * np.abs(base))
+
+
+def test_full_config_batch_is_deterministic_and_consistent(engine):
+    """BASELINE config 2 shape (1 star, N=2048, 1024 proposals per launch): same answers from a 1024-row launch,
+    from 148-row launches and run twice; a sample is checked against the oracle."""
+    n, B = 2048, 1024
+    t, y, yerr, _ = synthetic_lightcurve(2, n, kind="harmonic")
+    th = o.sample_from_prior(B, seed=33)
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    full = engine.lnlike_batch(th, lc_id=lc)
+    again = engine.lnlike_batch(th, lc_id=lc)
+    assert np.array_equal(full, again)
+    part = np.concatenate([engine.lnlike_batch(th[i:i + 148], lc_id=lc) for i in (0, 148)])
+    assert np.array_equal(part, full[:296])
+    idx = [0, 500, 1023]
+    ref = np.array([o.lnlike_function(th[i], t, y, yerr) for i in idx])
+    check(full[idx], ref, [cond_of(th[i], t, yerr) for i in idx], "config-2 sample")
+    assert np.all(np.isfinite(full) | (full == -np.inf))
+
+
+def test_lnpost_batch_masks_rows_outside_the_prior(engine):
+    t, y, yerr, _ = synthetic_lightcurve(4, 300, baseline=400.0)
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    th = o.sample_from_prior(8, seed=4)
+    th[2, 0] = 1.0            # above the ln A bound
+    th[5, 1] = th[5, 4] - 0.1  # ln l < ln P
+    lp, ll = engine.lnpost_batch(th, o.DEFAULT_BOUNDS, o.DEFAULT_GP_PRIOR_MU, o.DEFAULT_GP_PRIOR_SIGMA, lc_id=lc)
+    want_lp = np.array([o.lnprior(x) for x in th])
+    assert np.array_equal(np.isfinite(lp), np.isfinite(want_lp))
+    assert np.allclose(lp[np.isfinite(lp)], want_lp[np.isfinite(lp)], rtol=1e-13)
+    assert ll[2] == -np.inf and ll[5] == -np.inf
+    ok = np.isfinite(lp)
+    ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th[ok]])
+    check(ll[ok], ref, [cond_of(x, t, yerr) for x in th[ok]])
+
+
+def test_model_surface_is_a_drop_in(engine):
+    """GPRotModel.lnlike / lnprior / lnpost / lnlike_function on the engine vs the oracle, chunked and not."""
+    from gprotation_b200.fit import Emcee3Model, EnsemblePool, State
+    from gprotation_b200.lc import LightCurve
+    from gprotation_b200.model import GPRotModel
+
+    t, y, yerr, _ = synthetic_lightcurve(6, 900, baseline=900.0)
+    engine.unregister_all()
+    for cs in (300, None):
+        lc = LightCurve(t, y, yerr, chunksize=cs)
+        mod = GPRotModel(lc, engine=engine)
+        th = mod.sample_from_prior(5, seed=6)
+        chunks = o.split_chunks(len(t), cs)
+        for x in th:
+            want = o.lnlike(x, t, y, yerr, chunks)
+            assert abs(mod.lnlike(x) - want) <= 1e-9 * abs(want)
+            assert abs(mod.lnpost(x) - (want + o.lnprior(x))) <= 1e-9 * abs(want)
+        want = o.lnlike_function(th[0], t[:250], y[:250], yerr[:250])
+        assert abs(mod.lnlike_function(th[0], t[:250], y[:250], yerr[:250]) - want) <= 1e-9 * abs(want)
+        post = mod.lnpost_batch(th)
+        assert np.allclose(post, [o.lnpost(x, t, y, yerr, chunks) for x in th], rtol=1e-9)
+        walker = Emcee3Model(mod)
+        states = EnsemblePool().map(walker, [State(x) for x in th])
+        single = [walker(State(x)) for x in th]
+        for a, b in zip(states, single):
+            assert a.log_prior == pytest.approx(b.log_prior, rel=1e-13)
+            assert a.log_likelihood == pytest.approx(b.log_likelihood, rel=1e-12)
+
+
+def test_device_buffers_and_stream(engine):
+    """theta and out resident in HBM (torch tensors as plain pointers), launch on a torch stream."""
+    import torch
+
+    t, y, yerr, _ = synthetic_lightcurve(7, 400, baseline=500.0)
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    th = o.sample_from_prior(32, seed=12)
+    host = engine.lnlike_batch(th, lc_id=lc)
+    dth = torch.from_numpy(th).cuda()
+    dout = torch.empty(32, dtype=torch.float64, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        engine.lnlike_batch_device(dth.data_ptr(), 32, dout.data_ptr(), lc_id=lc, stream=st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(dout.cpu().numpy(), host)

@@ -1,0 +1,121 @@
+"""The oracle against its frozen fixtures, analytic known answers and independent evaluations (CPU only).
+
+The reference has no tests or golden vectors for this path and george is not installable
+offline: PARITY UNPINNED at the george boundary.  What is pinned here is the restated formula."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as o
+
+CASES = ["n24", "n64", "n150", "n300c100", "n257"]
+
+
+def _case(golden, name):
+    cs = int(golden[name + "_chunksize"])
+    t = golden[name + "_t"]
+    return t, golden[name + "_y"], golden[name + "_yerr"], golden[name + "_theta"], \
+        o.split_chunks(len(t), None if cs < 0 else cs)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_golden(golden, name):
+    t, y, yerr, thetas, chunks = _case(golden, name)
+    got = np.array([o.lnlike(th, t, y, yerr, chunks) for th in thetas])
+    ref = golden[name + "_lnlike"]
+    tol = 1e-12 * np.maximum(1.0, golden[name + "_cond"] / 1e3)      # LAPACK build differences scale with cond
+    assert np.all(np.abs(got - ref) <= tol * np.abs(ref))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_agrees_with_long_double_and_c(golden, name):
+    ref, cld, cf = golden[name + "_lnlike"], golden[name + "_lnlike_c_ld"], golden[name + "_lnlike_c_f64"]
+    tol = 1e-13 * np.maximum(1.0, golden[name + "_cond"])            # fp64 rounding ~ eps * cond
+    assert np.all(np.abs(ref - cld) <= tol * np.abs(cld))
+    assert np.all(np.abs(cf - cld) <= tol * np.abs(cld))
+
+
+def test_golden_agrees_with_mpmath(golden):
+    ref, mp = golden["n24_lnlike"], golden["n24_lnlike_mpmath"]
+    assert np.all(np.abs(ref - mp) <= 1e-12 * np.abs(mp))
+
+
+def test_c_oracle_matches_numpy_oracle(golden, oracle_c):
+    t, y, yerr, thetas, _ = _case(golden, "n150")
+    for th in thetas:
+        a = o.lnlike_function(th, t, y, yerr)
+        assert abs(oracle_c("f64", th, t, y, yerr) - a) <= 1e-10 * abs(a)
+        assert abs(oracle_c("ld", th, t, y, yerr) - a) <= 1e-10 * abs(a)
+
+
+def test_n1_closed_form():
+    th = np.array([-3.0, 5.0, -1.0, -4.0, 1.0])
+    A, L, G, S, P = np.exp(th)
+    t, y, e = np.array([3.7]), np.array([0.3]), np.array([0.05])
+    k = A + 2 * S + e[0] ** 2          # the white term counts twice (gprot/model.py:334 and :345-346)
+    want = -0.5 * (y[0] ** 2 / k + math.log(k) + math.log(2 * math.pi))
+    assert abs(o.lnlike_function(th, t, y, e) - want) < 1e-13 * abs(want)
+
+
+def test_n2_closed_form():
+    th = np.array([-2.0, 3.0, 0.5, -5.0, 0.7])
+    A, L, G, S, P = np.exp(th)
+    t, y, e = np.array([0.0, 1.3]), np.array([0.2, -0.4]), np.array([0.01, 0.02])
+    d = t[1] - t[0]
+    k01 = A * math.exp(-d * d / (2 * L)) * math.exp(-G * math.sin(math.pi * d / P) ** 2)
+    k00, k11 = A + 2 * S + e[0] ** 2, A + 2 * S + e[1] ** 2
+    det = k00 * k11 - k01 ** 2
+    quad = (k11 * y[0] ** 2 - 2 * k01 * y[0] * y[1] + k00 * y[1] ** 2) / det
+    want = -0.5 * (quad + math.log(det) + 2 * math.log(2 * math.pi))
+    assert abs(o.lnlike_function(th, t, y, e) - want) < 1e-12 * abs(want)
+
+
+def test_amplitude_to_zero_is_diagonal_gaussian():
+    rng = np.random.default_rng(0)
+    t = np.sort(rng.uniform(0, 50, 40))
+    y, e = rng.normal(size=40) * 0.01, np.full(40, 0.01)
+    th = np.array([-700.0, 5.0, -1.0, -9.0, 1.0])       # exp(-700) ~ 1e-304: K = diag(2S + e^2)
+    v = 2 * math.exp(-9.0) + e ** 2
+    want = -0.5 * np.sum(y ** 2 / v + np.log(v) + math.log(2 * math.pi))
+    assert abs(o.lnlike_function(th, t, y, e) - want) < 1e-12 * abs(want)
+
+
+def test_permutation_invariance_and_scaling(golden):
+    t, y, yerr, thetas, _ = _case(golden, "n64")
+    th = thetas[2]
+    base = o.lnlike_function(th, t, y, yerr)
+    p = np.random.default_rng(1).permutation(len(t))
+    assert abs(o.lnlike_function(th, t[p], y[p], yerr[p]) - base) < 1e-9 * abs(base)
+    c = 3.0                                               # y->cy, A->c^2 A, S->c^2 S, yerr->c yerr: lnlike -= N ln c
+    th2 = th.copy()
+    th2[0] += 2 * math.log(c)
+    th2[3] += 2 * math.log(c)
+    assert abs(o.lnlike_function(th2, t, c * y, c * yerr) - (base - len(t) * math.log(c))) < 1e-9 * abs(base)
+
+
+def test_chunk_sum_is_sum_of_independent_chunks(golden):
+    t, y, yerr, thetas, chunks = _case(golden, "n300c100")
+    assert [len(c) for c in chunks] == [100, 100, 100]
+    for th in thetas[:3]:
+        parts = sum(o.lnlike_function(th, t[c], y[c], yerr[c]) for c in chunks)
+        assert o.lnlike(th, t, y, yerr, chunks) == pytest.approx(parts, rel=1e-14)
+    assert [len(c) for c in o.split_chunks(700, 300)] == [234, 233, 233]      # np.array_split, <= chunksize
+    assert o.split_chunks(700, None) is None
+
+
+def test_failure_is_minus_inf_never_nan(golden):
+    t, y, yerr, thetas, _ = _case(golden, "n24")
+    for bad in ([np.nan, 5, 0, -5, 1], [800.0, 5, 0, -5, 1], [-3, 5, 0, -5, np.nan]):
+        v = o.lnlike_function(np.array(bad, dtype=float), t, y, yerr)
+        assert v == -np.inf
+    # exactly singular: duplicated time stamp, no noise at all
+    t2 = np.array([1.0, 1.0, 2.0])
+    v = o.lnlike_function(np.array([0.0, 5.0, 0.0, -800.0, 1.0]), t2, np.array([0.1, 0.2, 0.3]), np.zeros(3))
+    assert v == -np.inf or np.isfinite(v)
+    assert not np.isnan(v)
+
+
+def test_flop_model():
+    assert o.flops_per_eval(2048) == pytest.approx(2.8696e9, rel=1e-4)
+    assert o.flops_per_eval(8192) == pytest.approx(1.83353e11, rel=1e-4)

@@ -27,8 +27,9 @@ def unpack_block(buf):
     B[row, col] = buf
     return B
 
-sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 200, 256, 300, 384, 1000]
-eng = GPEngine(0)
+if __name__ != "__main__": sizes = []
+else: sizes = [int(a) for a in sys.argv[1:]] or [64, 128, 200, 256, 300, 384, 1000]
+eng = GPEngine(0) if sizes else None
 for N in sizes:
     eng.unregister_all()
     t, y, yerr = make_lc(N, seed=N)
