@@ -11,7 +11,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgprot_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("GPROT_B200_LIB", "libgprot_b200.so"))
 
 THETA_ON_DEVICE = 1
 OUT_ON_DEVICE = 2
@@ -34,6 +34,7 @@ SIGNATURES = {
     "gprot_launch_count": (c_int64, [c_void_p]),
     "gprot_measure_dmma_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "gprot_debug_read_scratch": (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_void_p]),
+    "gprot_debug_read_timing": (c_int, [c_void_p, c_void_p]),
 }
 
 _lib = None

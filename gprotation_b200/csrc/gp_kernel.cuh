@@ -48,7 +48,9 @@ struct Smem {
     double zs[BS];                // z_J
     double yj[BS];                // ytilde_J
     double dinv[BS];              // 1 / diag(L_JJ)
-    double wt[64];                // inverse of the current 8 x 8 diagonal tile
+    double wt[128];               // inverse of the current / next 8 x 8 diagonal tile (double buffered)
+    double lpart[4];              // per-warp partial sums of log diag(L_JJ)
+    double etab[64];              // 2^(j/64)
     Hyp hyp;
     double qpart[4];              // per-warp partial sums of z_J^2 (fixed-order reduction: deterministic)
     unsigned long long full[STAGES];
@@ -75,7 +77,14 @@ struct Params {
     size_t lslot_stride;          // doubles
     double* vscratch;             // per-slot vectors: sin, cos, diag, ytilde (4 * npad_max)
     int npad_max;
+    long long* timing;            // [16] per-phase cycle totals of CTA 0 (only written when built with -DGPROT_TIMING)
 };
+
+#ifdef GPROT_TIMING
+#define TICK(k) do { if (tid == 0) { const long long now_ = clock64(); tim_[k] += now_ - tlast_; tlast_ = now_; } } while (0)
+#else
+#define TICK(k) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,11 +153,54 @@ __device__ __forceinline__ void store_tile_frag(double* blk, const double (&acc)
     }
 }
 
+// ---------------------------------------------------------------- exp for the covariance synthesis
+// 2^(j/64), correctly rounded (generated with mpmath); copied to shared memory at kernel start.
+__constant__ double EXP2_64TH[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+};
+
+// exp(x) for finite x <= 0, <= 1 ulp: x = (64 k + j) ln2/64 + r, |r| <= ln2/128, exp = 2^k * T[j] * (1 + p(r)),
+// p of degree 5 in Estrin form (truncation r^6/720 < 3.5e-17).  11 FP64-pipe instructions and a dependent chain of 9,
+// about half of the general-purpose exp(); the synthesis of a tile is a latency chain, so both matter.
+// Arguments below -700 are clamped (exp(-700) ~ 1e-304 is zero against any diagonal this model can have).
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
+    x = fmax(x, -700.0);
+    const double MAGIC = 0x1.8p+52;
+    const double t = fma(x, 0x1.71547652b82fep+6, MAGIC);          // 64/ln2
+    const int ki = __double2loint(t);                               // 64 k + j (two's complement, <= 0)
+    const double kf = t - MAGIC;
+    double r = fma(kf, -0x1.62e42fee00000p-7, x);                   // ln2/64 split hi (32 bits) + lo
+    r = fma(kf, -0x1.a39ef35793c76p-39, r);
+    const double r2 = r * r;
+    const double a = fma(r, 0x1.5555555555555p-3, 0.5);             // 1/2 + r/6
+    const double b = fma(r, 0x1.1111111111111p-7, 0x1.5555555555555p-5);   // 1/24 + r/120
+    const double pp = fma(r2, fma(r2, b, a), r);
+    const double tj = tab[ki & 63];
+    const double res = fma(tj, pp, tj);
+    return __hiloint2double(__double2hiint(res) + ((ki >> 6) << 20), __double2loint(res));
+}
+
 // ---------------------------------------------------------------- covariance synthesis
 // EXACT: george's operation order, entry by entry (oracle/gp_oracle.py kernel_matrix).
 // fast : sin(pi (ti-tj)/P) = si*cj - ci*sj from per-point phases reduced in double-double, one exp.
 template <bool EXACT>
-__device__ __forceinline__ double kentry(double ti, double tj, double si, double ci, double sj, double cj, const Hyp& h) {
+__device__ __forceinline__ double kentry(double ti, double tj, double si, double ci, double sj, double cj, const Hyp& h,
+                                         const double* __restrict__ etab) {
     const double d = ti - tj;
     if (EXACT) {
         const double r2 = __ddiv_rn(__dmul_rn(d, d), h.L);
@@ -158,7 +210,7 @@ __device__ __forceinline__ double kentry(double ti, double tj, double si, double
         return __dmul_rn(__dmul_rn(h.A, e1), e2);
     } else {
         const double sn = si * cj - ci * sj;
-        return h.A * exp(fma(-h.G * sn, sn, -(d * d) * h.hl));
+        return h.A * exp_neg(fma(-h.G * sn, sn, -(d * d) * h.hl), etab);
     }
 }
 
@@ -167,7 +219,7 @@ __device__ __forceinline__ double kentry(double ti, double tj, double si, double
 template <bool EXACT, bool GENERAL>
 __device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], int row0, int col0, int n, const double* __restrict__ t,
                                            const double* vs, const double* vc,
-                                           const double* vd, const Hyp& h, bool white_off, int lane) {
+                                           const double* vd, const Hyp& h, const double* __restrict__ etab, bool white_off, int lane) {
     const int g = lane >> 2, q = lane & 3;
     double ti[4], si[4], ci[4];
 #pragma unroll
@@ -186,7 +238,7 @@ __device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], int row0, int
             const double sj = vs[c], cj = vc[c];
 #pragma unroll
             for (int mi = 0; mi < 4; mi++) {
-                double k = kentry<EXACT>(ti[mi], tj, si[mi], ci[mi], sj, cj, h);
+                double k = kentry<EXACT>(ti[mi], tj, si[mi], ci[mi], sj, cj, h, etab);
                 if (GENERAL) {
                     const int r = row0 + 8 * mi + g;
                     const double d = ti[mi] - tj;
@@ -237,14 +289,25 @@ __device__ __forceinline__ void accumulate(Smem& sm, double (&acc)[4][4][2], uin
                 for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+                if (DIAG && wr == wc) {                            // symmetric tile: 10 of the 16 8x8 sub-tiles
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++)
+                    for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+                        for (int ni = 0; ni <= mi; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++)
+                    for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+                        for (int ni = 0; ni <= mi; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+                } else {
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+                }
             }
         }
         __syncwarp();
@@ -260,74 +323,112 @@ __device__ __forceinline__ void accumulate(Smem& sm, double (&acc)[4][4][2], uin
 // (i)   warp 0 factors the 8 x 8 diagonal tile and inverts it in registers;
 // (ii)  every other tile row of the panel is multiplied by the tile inverse (2 DMMAs per tile);
 // (iii) all tiles right of the panel receive the rank-8 update (2 DMMAs per tile).
-__device__ __forceinline__ void tile8_factor(Smem& sm, int p, int lane, double& logdet) {
+// 1/sqrt(d) for a positive, finite, normal d: MUFU.RSQ64H seed (2^-22.9) and one third-order correction
+// (error ~ (5/16) e^3 ~ 2^-70), branch free -- the 8 x 8 tile factorisation below is a pure latency chain.
+__device__ __forceinline__ double rsqrt_pos(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-(d * y), y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
+
+// Factor the 8 x 8 diagonal tile p of M (lower triangle) and invert it, one row per lane (lanes 8..31 mirror
+// lanes 0..7 so that shuffles stay warp-uniform).  Column j: the pivot is broadcast from lane j, every lane forms
+// 1/sqrt itself, scales its entry of the column and eliminates it from its row; the same elimination applied to
+// the rows of an identity yields the inverse (Gauss-Jordan on a triangular matrix), off the pivot's critical path.
+// (A register-resident variant without shuffles is faster in isolation -- 1.5k vs 2.1k cycles -- but needs ~110
+// registers on top of the kernel's live state and spills under the 128-register cap of a 512-thread CTA.)
+// Results: L_pp (lower, in M), W_pp^T (strict upper, in M), W_pp (sm.wt[buf], zero above the diagonal), 1/diag (sm.dinv).
+__device__ __forceinline__ void tile8_factor(Smem& sm, int p, int buf, int lane) {
     double* Mp = sm.regionA + (8 * p) * LDM + 8 * p;
-    double l[8][8];
+    const int a = lane & 7;
+    double row[8], inv[8];
+    {
+        const double2* src = reinterpret_cast<const double2*>(Mp + a * LDM);
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+        for (int c = 0; c < 4; c++) {
+            const double2 v = src[c];
+            row[2 * c] = v.x;
+            row[2 * c + 1] = v.y;
+        }
+    }
 #pragma unroll
-        for (int b = 0; b <= a; b++) l[a][b] = Mp[a * LDM + b];
-    double rinv[8];
+    for (int c = 0; c < 8; c++) inv[c] = (c == a) ? 1.0 : 0.0;
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const double d = l[j][j];
+        const double d = __shfl_sync(0xffffffffu, row[j], j);
         if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
-        const double ljj = sqrt(d);
-        const double ri = 1.0 / ljj;
-        l[j][j] = ljj;
-        rinv[j] = ri;
+        const double ri = rsqrt_pos(d);
+        double ljj = d * ri;
+        ljj = fma(fma(-ljj, ljj, d), 0.5 * ri, ljj);       // one Newton step on sqrt: <= 1 ulp
+        const double lj = (a == j) ? ljj : row[j] * ri;     // column j of L, one entry per lane (rows a >= j)
+        row[j] = lj;
 #pragma unroll
-        for (int a = j + 1; a < 8; a++) l[a][j] *= ri;
-#pragma unroll
-        for (int a = j + 1; a < 8; a++)
-#pragma unroll
-            for (int b = j + 1; b <= a; b++) l[a][b] = fma(-l[a][j], l[b][j], l[a][b]);
-    }
-    // column b = lane & 7 of the inverse: w_b = 1/l_bb, w_a = -(sum_{m<a} l_am w_m)/l_aa (w_m = 0 for m < b)
-    const int b = lane & 7;
-    double w[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) {
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < a; m++) s = fma(l[a][m], w[m], s);
-        w[a] = (a == b) ? rinv[a] : ((a > b) ? -rinv[a] * s : 0.0);
-    }
-    __syncwarp();
-    if (lane < 8) {
-#pragma unroll
-        for (int a = 0; a < 8; a++) {
-            sm.wt[a * 8 + b] = w[a];                        // W_pp[a][b], zeros above the diagonal
-            if (a > b) Mp[b * LDM + a] = w[a];              // strict upper of the tile: W_pp^T
+        for (int b = j + 1; b < 8; b++) {                   // l[a][b] -= l[a][j] * l[b][j]   (used for a >= b)
+            const double cb = __shfl_sync(0xffffffffu, lj, b);
+            row[b] = fma(-lj, cb, row[b]);
         }
-        sm.dinv[8 * p + b] = w[b];
+        // inverse rows: Y[j][:] *= 1/l_jj ; Y[a][:] -= l[a][j] * Y[j][:] for a > j   (Y starts as I, ends as L^-1)
 #pragma unroll
-        for (int a = 0; a < 8; a++)
-            if (a == b) {
-#pragma unroll
-                for (int c = 0; c <= a; c++) Mp[a * LDM + c] = l[a][c];
-            }
+        for (int c = 0; c <= j; c++) {
+            const double yj = __shfl_sync(0xffffffffu, inv[c] * ri, j);
+            inv[c] = (a == j) ? yj : ((a > j) ? fma(-lj, yj, inv[c]) : inv[c]);
+        }
     }
-    if (lane == 0) {
+    if (lane < 8) {
+        double* wt = sm.wt + 64 * buf;
 #pragma unroll
-        for (int a = 0; a < 8; a++) logdet += log(l[a][a]);
-        if (bad) sm.fail = 1;
+        for (int c = 0; c < 8; c++) {
+            const double w = (c <= a) ? inv[c] : 0.0;
+            wt[a * 8 + c] = w;                              // W_pp[a][c], zeros above the diagonal
+            if (c < a) Mp[c * LDM + a] = w;                 // strict upper of the tile: W_pp^T
+            if (c == a) sm.dinv[8 * p + a] = w;
+            if (c <= a) Mp[a * LDM + c] = row[c];           // L_pp
+        }
     }
+    if (bad && lane == 0) sm.fail = 1;
 }
 
-__device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, double& logdet) {
-    const int g = lane >> 2, q = lane & 3;
+// one rank-8 update task of step p: tile (R, C) -= X(R) * L(C, p)^T
+__device__ __forceinline__ void tile8_update(Smem& sm, int p, int R, int C, int g, int q) {
     double* M = sm.regionA;
+    const int P0 = 8 * p;
+    double a0, a1;
+    if (R == p) {                                           // rows of the diagonal tile act through W_pp^T
+        const double* wt = sm.wt + 64 * (p & 1);
+        a0 = wt[q * 8 + g];
+        a1 = wt[(q + 4) * 8 + g];
+    } else {
+        const double* ar = M + (8 * R + g) * LDM + P0;
+        a0 = ar[q];
+        a1 = ar[q + 4];
+    }
+    const double* br = M + (8 * C + g) * LDM + P0;
+    const double b0 = br[q], b1 = br[q + 4];
+    double2* cp = reinterpret_cast<double2*>(M + (8 * R + g) * LDM + 8 * C + 2 * q);
+    double2 c = *cp;
+    dmma(c.x, c.y, -a0, b0);
+    dmma(c.x, c.y, -a1, b1);
+    *cp = c;
+}
+
+__device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, long long* tim_, long long& tlast_) {
+    const int g = lane >> 2, q = lane & 3;
+    const int tid = threadIdx.x;
+    (void)tid; (void)tim_; (void)tlast_;
+    double* M = sm.regionA;
+    if (warp == 0) tile8_factor(sm, 0, 0, lane);
+    TICK(12);
+    __syncthreads();
     for (int p = 0; p < 16; p++) {
         const int P0 = 8 * p;
-        if (warp == 0) tile8_factor(sm, p, lane, logdet);
-        __syncthreads();
         // (ii) tile row `warp` of the panel: X = M(warp, p) * W_pp^T
         if (warp != p) {
+            const double* wt = sm.wt + 64 * (p & 1);
             double* row = M + (8 * warp + g) * LDM + P0;
             const double a0 = row[q], a1 = row[q + 4];
-            const double b0 = sm.wt[g * 8 + q], b1 = sm.wt[g * 8 + q + 4];
+            const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
             double c0 = 0.0, c1 = 0.0;
             dmma(c0, c1, a0, b0);
             dmma(c0, c1, a1, b1);
@@ -335,40 +436,37 @@ __device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, double
             *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
         }
         __syncthreads();
-        // (iii) rank-8 update of tiles (R, C), C > p, R in [0..p] (inverse rows) or [C..15] (Schur complement)
+        TICK(13);
+        if (p == 15) break;
+        // (iii) rank-8 update of tiles (R, C), C > p, R in [0..p] (inverse rows) or [C..15] (Schur complement).
+        // Warp 0 updates the next diagonal tile first and factors it right away (look-ahead): the 8 x 8
+        // elimination is the critical path of the sweep, the other 15 warps share the remaining tiles.
         const int ncol = 15 - p;
         const int nrect = (p + 1) * ncol;
         const int ntask = nrect + ncol * (ncol + 1) / 2;
-        for (int task = warp; task < ntask; task += 16) {
-            int R, C;
-            if (task < nrect) {
-                R = task / ncol;
-                C = p + 1 + task % ncol;
-            } else {
-                const int u = task - nrect;
-                int i = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
-                while ((i + 1) * (i + 2) / 2 <= u) i++;
-                while (i * (i + 1) / 2 > u) i--;
-                R = p + 1 + i;
-                C = p + 1 + (u - i * (i + 1) / 2);
+        if (warp == 0) {
+            tile8_update(sm, p, p + 1, p + 1, g, q);
+            __syncwarp();
+            tile8_factor(sm, p + 1, (p + 1) & 1, lane);
+        } else {
+            for (int task = warp - 1; task < ntask - 1; task += 15) {
+                const int tk = task < nrect ? task : task + 1;   // skip task nrect = tile (p+1, p+1)
+                int R, C;
+                if (tk < nrect) {
+                    R = tk / ncol;
+                    C = p + 1 + tk % ncol;
+                } else {
+                    const int u = tk - nrect;
+                    int i = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
+                    while ((i + 1) * (i + 2) / 2 <= u) i++;
+                    while (i * (i + 1) / 2 > u) i--;
+                    R = p + 1 + i;
+                    C = p + 1 + (u - i * (i + 1) / 2);
+                }
+                tile8_update(sm, p, R, C, g, q);
             }
-            double a0, a1;
-            if (R == p) {                                   // rows of the diagonal tile act through W_pp^T
-                a0 = sm.wt[q * 8 + g];
-                a1 = sm.wt[(q + 4) * 8 + g];
-            } else {
-                const double* ar = M + (8 * R + g) * LDM + P0;
-                a0 = ar[q];
-                a1 = ar[q + 4];
-            }
-            const double* br = M + (8 * C + g) * LDM + P0;
-            const double b0 = br[q], b1 = br[q + 4];
-            double2* cp = reinterpret_cast<double2*>(M + (8 * R + g) * LDM + 8 * C + 2 * q);
-            double2 c = *cp;
-            dmma(c.x, c.y, -a0, b0);
-            dmma(c.x, c.y, -a1, b1);
-            *cp = c;
         }
+        TICK(14);
         __syncthreads();
     }
 }
@@ -382,6 +480,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
     const int wr = warp >> 2, wc = ((warp & 3) - (warp >> 2)) & 3;   // skewed so each scheduler sees every wc
     const int g = lane >> 2, q = lane & 3;
 
+    if (tid < 64) sm.etab[tid] = EXP2_64TH[tid];
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&sm.full[s], 1);
@@ -392,6 +491,9 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
     __syncthreads();
 
     uint32_t it = 0;   // pipeline iteration counter (uniform across the CTA)
+#ifdef GPROT_TIMING
+    long long tim_[16] = {0}, tlast_ = clock64();
+#endif
     double* const lbase = prm.lscratch + (size_t)blockIdx.x * prm.lslot_stride;
     double* const vs = prm.vscratch + (size_t)blockIdx.x * 4 * prm.npad_max;
     double* const vc = vs + prm.npad_max;
@@ -407,6 +509,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         __syncthreads();
         const int prob = sm.prob;
         if (prob >= prm.nprob) break;
+        TICK(15);
 
         const int chunk = prm.prob_chunk[prob];
         const int n = prm.chunk_n[chunk];
@@ -427,7 +530,14 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         }
         __syncthreads();
         const Hyp& h = sm.hyp;
-        const bool white_off = prm.chunk_mingap2[chunk] < h.thr;
+        const double mingap2 = prm.chunk_mingap2[chunk];            // < 0 flags a chunk with non-finite t or yerr
+        // a non-finite or non-positive scale makes K non-finite or singular by construction: the reference returns -inf
+        if (!(h.A >= 0.0 && h.A <= DBL_MAX && h.L > 0.0 && h.L <= DBL_MAX && h.G >= 0.0 && h.G <= DBL_MAX &&
+              h.S >= 0.0 && h.S <= DBL_MAX && h.P > 0.0 && h.P <= DBL_MAX && mingap2 >= 0.0)) {
+            if (tid == 0) prm.prob_out[prob] = -INFINITY;
+            continue;
+        }
+        const bool white_off = mingap2 < h.thr;
         // per-point vectors: phase of t_i / P reduced in double-double, diagonal noise, working copy of y
         for (int i = tid; i < npad; i += NT) {
             double s = 0.0, c = 1.0, dg = 0.0, yy = 0.0;
@@ -444,6 +554,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
         }
         __syncthreads();
+        TICK(0);
 
         double logdet = 0.0, quad = 0.0;     // sum log diag(L) and |z|^2, meaningful in thread 0
         double acc[4][4][2];
@@ -456,9 +567,11 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             {
                 const bool active = wr >= wc;
                 if (tid == 0) prologue<true>(sm, it, jrow, jrow, niter);
-                if (active) synth_tile<EXACT, true>(acc, J * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, white_off, lane);
+                if (active) synth_tile<EXACT, true>(acc, J * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
+                TICK(1);
                 accumulate<true>(sm, acc, it, jrow, jrow, niter, wr, wc, lane, active);
                 __syncthreads();                                   // all stages consumed: regionA becomes M
+                TICK(2);
                 {
                     double* M = sm.regionA;
 #pragma unroll
@@ -474,7 +587,13 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                     if (tid < BS) sm.yj[tid] = yw[J * BS + tid];
                 }
                 __syncthreads();
-                diag_factor(sm, warp, lane, logdet);               // ends with __syncthreads
+                TICK(3);
+#ifdef GPROT_TIMING
+                diag_factor(sm, warp, lane, tim_, tlast_);         // ends with __syncthreads
+#else
+                { long long dummy_ = 0; diag_factor(sm, warp, lane, nullptr, dummy_); }
+#endif
+                TICK(4);
                 if (sm.fail) { failed = true; break; }
                 // W -> B-operand fragments (zeros above the diagonal of each 16 x 16 corner), z_J = W ytilde_J
                 {
@@ -503,25 +622,36 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                         const double z = ((s0 + s1) + (s2 + s3)) + sm.dinv[r] * sm.yj[r];
                         sm.zs[r] = z;
                         double z2 = z * z;
+                        double lg = -log(sm.dinv[r]);               // log L_rr (identity padding gives exactly 0)
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) z2 += __shfl_xor_sync(0xffffffffu, z2, o);
-                        if (lane == 0) sm.qpart[warp] = z2;
+                        for (int o = 16; o > 0; o >>= 1) {
+                            z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+                            lg += __shfl_xor_sync(0xffffffffu, lg, o);
+                        }
+                        if (lane == 0) { sm.qpart[warp] = z2; sm.lpart[warp] = lg; }
                     }
                 }
                 fence_async();
                 __syncthreads();
-                if (tid == 0) quad += (sm.qpart[0] + sm.qpart[1]) + (sm.qpart[2] + sm.qpart[3]);
+                TICK(5);
+                if (tid == 0) {
+                    quad += (sm.qpart[0] + sm.qpart[1]) + (sm.qpart[2] + sm.qpart[3]);
+                    logdet += (sm.lpart[0] + sm.lpart[1]) + (sm.lpart[2] + sm.lpart[3]);
+                    if (J + 1 < T) prologue<false>(sm, it, lbase + (size_t)((J + 1) * J / 2) * BLKD, jrow, niter);
+                }
             }
-            // ================= blocks below the diagonal
+            // ================= blocks below the diagonal (their first slabs are already in flight)
             for (int I = J + 1; I < T; I++) {
                 const double* irow = lbase + (size_t)(I * (I - 1) / 2) * BLKD;
-                if (tid == 0) prologue<false>(sm, it, irow, jrow, niter);
-                if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, white_off, lane);
-                else                                synth_tile<EXACT, true>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, white_off, lane);
+                if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
+                else                                synth_tile<EXACT, true>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
+                TICK(6);
                 accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, true);
                 __syncthreads();                                   // stages drained: regionA becomes the S_IJ staging block
+                TICK(7);
                 store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc
                 __syncthreads();
+                TICK(8);
                 // ---- L_IJ = S W^T : k runs over m <= c
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++)
@@ -587,16 +717,25 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                         if (q == 0) sm.red[wc * BS + 32 * wr + 8 * mi + g] = part[mi];
                     }
                 }
-                __syncthreads();                                   // staging reads done, partials visible
+                // stored as each warp finishes: warps with a short triangular product overlap their stores with the
+                // others' DMMAs
                 store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
+                fence_async();
+                __syncthreads();                                   // staging reads done (regionA free again), partials visible
+                TICK(9);
+                if (tid == 0 && I + 1 < T)                         // next block's first slabs fly during its synthesis
+                    prologue<false>(sm, it, lbase + (size_t)((I + 1) * I / 2) * BLKD, jrow, niter);
                 if (tid < BS) {
                     const int r = tid;
                     yw[I * BS + r] -= (sm.red[r] + sm.red[BS + r]) + (sm.red[2 * BS + r] + sm.red[3 * BS + r]);
                 }
-                __threadfence();
-                fence_async();
-                __syncthreads();
+                TICK(10);
             }
+            // blocks of column J are first read (by TMA, the async proxy) in column J+1: one fence per column
+            __threadfence();
+            fence_async();
+            __syncthreads();
+            TICK(11);
         }
         if (tid == 0) {
             double lnl;
@@ -608,6 +747,10 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             prm.prob_out[prob] = lnl;
         }
     }
+#ifdef GPROT_TIMING
+    if (tid == 0 && blockIdx.x == 0 && prm.timing)
+        for (int k = 0; k < 16; k++) prm.timing[k] = tim_[k];
+#endif
 }
 
 // out[b] = sum over the row's problems, in a fixed order (gprot/model.py:362-365 np.sum over chunks)

@@ -37,6 +37,7 @@ struct gprot_ctx {
     double* d_prob_out = nullptr;
     int *d_row_first = nullptr, *d_row_count = nullptr; size_t cap_rows = 0;
     int* d_counter = nullptr;
+    long long* d_timing = nullptr;
     // work-slot scratch
     double* d_lscratch = nullptr; size_t lslot_stride = 0; int lslots = 0;
     double* d_vscratch = nullptr; int v_npad = 0; int vslots = 0;
@@ -249,6 +250,7 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
         prm.counter = ctx->d_counter;
         prm.lscratch = ctx->d_lscratch; prm.lslot_stride = ctx->lslot_stride;
         prm.vscratch = ctx->d_vscratch; prm.npad_max = ctx->v_npad;
+        prm.timing = ctx->d_timing;
         CU(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
         CU(ctx, cudaEventRecord(ctx->ev0, st));
         if (flags & GPROT_EXACT_KERNEL) gp_lnlike_kernel<true><<<slots, NT, sizeof(Smem), st>>>(prm);
@@ -297,7 +299,7 @@ int gprot_create(int device, gprot_ctx** out) {
         return fail(nullptr, "gprot_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(p.major) + std::to_string(p.minor));
     }
     ctx->num_sms = p.multiProcessorCount;
-    if (cudaMalloc((void**)&ctx->d_counter, 64) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+    if (cudaMalloc((void**)&ctx->d_counter, 64) != cudaSuccess || cudaMalloc((void**)&ctx->d_timing, 16 * 8) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
         cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, "context allocation failed");
@@ -312,7 +314,7 @@ int gprot_destroy(gprot_ctx* ctx) {
     cudaDeviceSynchronize();
     void* ptrs[] = {ctx->d_t, ctx->d_y, ctx->d_yerr, ctx->d_chunk_mingap2, ctx->d_chunk_off, ctx->d_chunk_n, ctx->d_theta,
                     ctx->d_out, ctx->d_prob_theta, ctx->d_prob_chunk, ctx->d_prob_out, ctx->d_row_first, ctx->d_row_count,
-                    ctx->d_counter, ctx->d_lscratch, ctx->d_vscratch};
+                    ctx->d_counter, ctx->d_lscratch, ctx->d_vscratch, ctx->d_timing};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -341,6 +343,8 @@ int gprot_register_lc(gprot_ctx* ctx, int m, const int* n, const double* t, cons
             const double d = s[i] - s[i - 1];
             g2 = std::min(g2, d * d);
         }
+        for (int i = 0; i < n[c]; i++)                       // non-finite stamps or errors: the chunk evaluates to -inf
+            if (!std::isfinite(t[pos + i]) || !std::isfinite(yerr[pos + i])) g2 = -1.0;
         ctx->h_chunk_mingap2.push_back(g2);
         ctx->h_t.insert(ctx->h_t.end(), t + pos, t + pos + n[c]);
         ctx->h_y.insert(ctx->h_y.end(), y + pos, y + pos + n[c]);
@@ -438,6 +442,14 @@ int gprot_measure_dmma_peak(gprot_ctx* ctx, double* tflops, double* sm_clock_mhz
     if (sm_clock_mhz) *sm_clock_mhz = (double)c / (best * 1e-3) / 1e6;
     cudaFree(out); cudaFree(cyc); cudaEventDestroy(e0); cudaEventDestroy(e1);
     ctx->launches += 4;
+    return 0;
+}
+
+int gprot_debug_read_timing(gprot_ctx* ctx, long long* host_out16) {
+    if (!ctx || !host_out16) return fail(ctx, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemcpy(host_out16, ctx->d_timing, 16 * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -89,6 +89,10 @@ int gprot_measure_dmma_peak(gprot_ctx *ctx, double *tflops, double *sm_clock_mhz
  * (fragment-major 128 x 128 blocks, strictly-lower block rows). */
 int gprot_debug_read_scratch(gprot_ctx *ctx, int slot, size_t offset, size_t count, double *host_out);
 
+/* Test hook: per-phase SM-cycle totals of CTA 0 for the last launch; all zero unless the library was built with
+ * -DGPROT_TIMING (tools/dev_timing.py builds that variant next to the product library). */
+int gprot_debug_read_timing(gprot_ctx *ctx, long long *host_out16);
+
 #ifdef __cplusplus
 }
 #endif
