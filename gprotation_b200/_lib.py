@@ -30,6 +30,8 @@ SIGNATURES = {
     "gprot_lnpost_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
                                    c_void_p, c_int, c_void_p, c_void_p, c_uint, c_void_p]),
     "gprot_sync": (c_int, [c_void_p]),
+    "gprot_set_cluster": (c_int, [c_void_p, c_int]),
+    "gprot_last_cluster": (c_int, [c_void_p]),
     "gprot_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "gprot_launch_count": (c_int64, [c_void_p]),
     "gprot_measure_dmma_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),

@@ -117,6 +117,21 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t by
 }
 // order generic-proxy accesses (st.global / ld.shared / st.shared) before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// thread-block cluster: rank, barrier with release/acquire at cluster scope (orders global and shared::cluster
+// accesses of all CTAs of the cluster), store into a peer CTA's shared memory (DSMEM)
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dsmem_store_int(int* local, uint32_t peer, int v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(peer));
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
 
 // ---------------------------------------------------------------- layouts
 // Fragment-major operand layout.  A 128 x 16 slab is stored as [row group 16][k pair 2][lane 32][2]:
@@ -472,7 +487,11 @@ __device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, long l
 }
 
 // ---------------------------------------------------------------- the kernel
-template <bool EXACT>
+// CL = CTAs per problem.  CL > 1 launches thread-block clusters of CL CTAs that share one problem: every CTA forms the
+// diagonal block of a column (redundantly: same operands, same order, bitwise the same W and z_J -- the CTAs would
+// otherwise wait for it), block row I below the diagonal belongs to CTA I mod CL, and one cluster barrier per column
+// publishes the new blocks of L and the updated right-hand side.  Results are bitwise identical for every CL.
+template <bool EXACT, int CL>
 __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -494,8 +513,10 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
 #ifdef GPROT_TIMING
     long long tim_[16] = {0}, tlast_ = clock64();
 #endif
-    double* const lbase = prm.lscratch + (size_t)blockIdx.x * prm.lslot_stride;
-    double* const vs = prm.vscratch + (size_t)blockIdx.x * 4 * prm.npad_max;
+    const int crank = CL > 1 ? (int)cluster_rank() : 0;
+    const int slot = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+    double* const lbase = prm.lscratch + (size_t)slot * prm.lslot_stride;
+    double* const vs = prm.vscratch + (size_t)slot * 4 * prm.npad_max;
     double* const vc = vs + prm.npad_max;
     double* const vd = vc + prm.npad_max;
     double* const yw = vd + prm.npad_max;
@@ -503,10 +524,14 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            sm.prob = atomicAdd(prm.counter, 1);
+            if (CL == 1) sm.prob = atomicAdd(prm.counter, 1);
+            else if (crank == 0) {
+                const int p = atomicAdd(prm.counter, 1);
+                for (int c = 0; c < CL; c++) dsmem_store_int(&sm.prob, c, p);
+            }
             sm.fail = 0;
         }
-        __syncthreads();
+        if (CL > 1) cluster_sync(); else __syncthreads();
         const int prob = sm.prob;
         if (prob >= prm.nprob) break;
         TICK(15);
@@ -534,12 +559,12 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         // a non-finite or non-positive scale makes K non-finite or singular by construction: the reference returns -inf
         if (!(h.A >= 0.0 && h.A <= DBL_MAX && h.L > 0.0 && h.L <= DBL_MAX && h.G >= 0.0 && h.G <= DBL_MAX &&
               h.S >= 0.0 && h.S <= DBL_MAX && h.P > 0.0 && h.P <= DBL_MAX && mingap2 >= 0.0)) {
-            if (tid == 0) prm.prob_out[prob] = -INFINITY;
+            if (tid == 0 && crank == 0) prm.prob_out[prob] = -INFINITY;
             continue;
         }
         const bool white_off = mingap2 < h.thr;
         // per-point vectors: phase of t_i / P reduced in double-double, diagonal noise, working copy of y
-        for (int i = tid; i < npad; i += NT) {
+        for (int i = crank * NT + tid; i < npad; i += CL * NT) {
             double s = 0.0, c = 1.0, dg = 0.0, yy = 0.0;
             if (i < n) {
                 const double ti = t[i];
@@ -553,7 +578,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             }
             vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
         }
-        __syncthreads();
+        if (CL > 1) cluster_sync(); else __syncthreads();
         TICK(0);
 
         double logdet = 0.0, quad = 0.0;     // sum log diag(L) and |z|^2, meaningful in thread 0
@@ -637,11 +662,13 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 if (tid == 0) {
                     quad += (sm.qpart[0] + sm.qpart[1]) + (sm.qpart[2] + sm.qpart[3]);
                     logdet += (sm.lpart[0] + sm.lpart[1]) + (sm.lpart[2] + sm.lpart[3]);
-                    if (J + 1 < T) prologue<false>(sm, it, lbase + (size_t)((J + 1) * J / 2) * BLKD, jrow, niter);
                 }
             }
+            // first block row of this column owned by this CTA (rows are dealt round-robin: I mod CL)
+            const int I0 = CL > 1 ? J + 1 + ((crank - (J + 1)) % CL + CL) % CL : J + 1;
+            if (tid == 0 && I0 < T) prologue<false>(sm, it, lbase + (size_t)(I0 * (I0 - 1) / 2) * BLKD, jrow, niter);
             // ================= blocks below the diagonal (their first slabs are already in flight)
-            for (int I = J + 1; I < T; I++) {
+            for (int I = I0; I < T; I += CL) {
                 const double* irow = lbase + (size_t)(I * (I - 1) / 2) * BLKD;
                 if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
                 else                                synth_tile<EXACT, true>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
@@ -723,8 +750,8 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 fence_async();
                 __syncthreads();                                   // staging reads done (regionA free again), partials visible
                 TICK(9);
-                if (tid == 0 && I + 1 < T)                         // next block's first slabs fly during its synthesis
-                    prologue<false>(sm, it, lbase + (size_t)((I + 1) * I / 2) * BLKD, jrow, niter);
+                if (tid == 0 && I + CL < T)                        // next block's first slabs fly during its synthesis
+                    prologue<false>(sm, it, lbase + (size_t)((I + CL) * (I + CL - 1) / 2) * BLKD, jrow, niter);
                 if (tid < BS) {
                     const int r = tid;
                     yw[I * BS + r] -= (sm.red[r] + sm.red[BS + r]) + (sm.red[2 * BS + r] + sm.red[3 * BS + r]);
@@ -734,10 +761,10 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             // blocks of column J are first read (by TMA, the async proxy) in column J+1: one fence per column
             __threadfence();
             fence_async();
-            __syncthreads();
+            if (CL > 1) { cluster_sync(); fence_async(); } else __syncthreads();
             TICK(11);
         }
-        if (tid == 0) {
+        if (tid == 0 && crank == 0) {
             double lnl;
             if (failed) lnl = -INFINITY;
             else {

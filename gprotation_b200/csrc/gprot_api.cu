@@ -47,6 +47,9 @@ struct gprot_ctx {
     float last_ms = 0.f;
     int64_t launches = 0;
     bool attr_set = false;
+    int force_cluster = 0;            // 0 = choose per launch; 1, 2, 4, 8 = CTAs per problem
+    int max_clusters[9] = {0};        // co-resident clusters of each size (cudaOccupancyMaxActiveClusters), 0 = unknown
+    int last_cluster = 1;
 };
 
 namespace {
@@ -128,6 +131,65 @@ double lnprior_one(const double* th, const double* bounds, const double* mu, con
     return lnpr;
 }
 
+typedef void (*kernel_fn)(const Params);
+kernel_fn kernel_for(bool exact, int cl) {
+    switch (cl) {
+        case 2: return exact ? gp_lnlike_kernel<true, 2> : gp_lnlike_kernel<false, 2>;
+        case 4: return exact ? gp_lnlike_kernel<true, 4> : gp_lnlike_kernel<false, 4>;
+        case 8: return exact ? gp_lnlike_kernel<true, 8> : gp_lnlike_kernel<false, 8>;
+        default: return exact ? gp_lnlike_kernel<true, 1> : gp_lnlike_kernel<false, 1>;
+    }
+}
+
+// Relative time of one problem of T block columns on a cluster of cl CTAs, in units of one 128^3 DMMA block product
+// (weights from the phase budget in DESIGN.md section 4): the diagonal block of a column is formed by every CTA,
+// the T-1-J blocks below it are dealt round-robin.
+double problem_time_model(int T, int cl) {
+    double t = 0.0;
+    for (int J = 0; J < T; J++) {
+        const int rows = T - 1 - J;
+        t += 0.6 * J + 4.0 + (double)((rows + cl - 1) / cl) * (J + 2.0) + (cl > 1 ? 0.05 : 0.0);
+    }
+    return t;
+}
+
+int query_clusters(gprot_ctx* ctx) {
+    if (ctx->max_clusters[1]) return 0;
+    ctx->max_clusters[1] = ctx->num_sms;
+    for (int cl : {2, 4, 8}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(ctx->num_sms / cl * cl));
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = sizeof(Smem);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, (void*)kernel_for(false, cl), &cfg);
+        if (e != cudaSuccess) { cudaGetLastError(); nc = 0; }
+        ctx->max_clusters[cl] = std::min(nc, ctx->num_sms / cl);
+    }
+    return 0;
+}
+
+// CTAs per problem for a launch of nprob problems whose largest has tmax block columns: the size that minimises
+// rounds x modelled time per problem.  Batches that fill the GPU (nprob >= SMs) with short tails stay at 1.
+int choose_cluster(gprot_ctx* ctx, int nprob, int tmax) {
+    if (ctx->force_cluster) return ctx->max_clusters[ctx->force_cluster] > 0 ? ctx->force_cluster : 1;
+    if (tmax < 3) return 1;
+    int best = 1;
+    double best_t = 0.0;
+    for (int cl : {1, 2, 4, 8}) {
+        const int nc = ctx->max_clusters[cl];
+        if (nc <= 0) continue;
+        const double rounds = (double)((nprob + nc - 1) / nc);
+        const double t = rounds * problem_time_model(tmax, cl);
+        if (cl == 1 || t < 0.97 * best_t) { best = cl; best_t = t; }
+    }
+    return best;
+}
+
 // core: likelihood of the rows of theta selected by mask (NULL = all)
 int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* lc_id, const unsigned char* mask,
                 double* out, unsigned flags, cudaStream_t st) {
@@ -207,7 +269,16 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
 
     if (nprob > 0) {
         // ---- work slots: one persistent CTA per SM, each with its own factor scratch
-        int slots = std::min(nprob, ctx->num_sms);
+        if (!ctx->attr_set) {
+            for (int cl : {1, 2, 4, 8})
+                for (int ex = 0; ex < 2; ex++)
+                    CU(ctx, cudaFuncSetAttribute((const void*)kernel_for(ex != 0, cl), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+            ctx->attr_set = true;
+        }
+        query_clusters(ctx);
+        const int cl = choose_cluster(ctx, nprob, tmax);
+        ctx->last_cluster = cl;
+        int slots = std::min(nprob, ctx->max_clusters[cl]);      // one slot per co-resident CTA group
         const size_t stride = std::max<size_t>((size_t)tmax * (tmax - 1) / 2, 1) * BLKD;
         const int npad = tmax * BS;
         if (stride > ctx->lslot_stride || slots > ctx->lslots) {
@@ -236,11 +307,6 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
             ctx->v_npad = np2;
             ctx->vslots = want;
         }
-        if (!ctx->attr_set) {
-            CU(ctx, cudaFuncSetAttribute(gp_lnlike_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-            CU(ctx, cudaFuncSetAttribute(gp_lnlike_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-            ctx->attr_set = true;
-        }
         Params prm;
         prm.t = ctx->d_t; prm.y = ctx->d_y; prm.yerr = ctx->d_yerr;
         prm.chunk_off = ctx->d_chunk_off; prm.chunk_n = ctx->d_chunk_n; prm.chunk_mingap2 = ctx->d_chunk_mingap2;
@@ -253,8 +319,18 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
         prm.timing = ctx->d_timing;
         CU(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
         CU(ctx, cudaEventRecord(ctx->ev0, st));
-        if (flags & GPROT_EXACT_KERNEL) gp_lnlike_kernel<true><<<slots, NT, sizeof(Smem), st>>>(prm);
-        else                            gp_lnlike_kernel<false><<<slots, NT, sizeof(Smem), st>>>(prm);
+        {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(slots * cl));
+            cfg.blockDim = dim3(NT);
+            cfg.dynamicSmemBytes = sizeof(Smem);
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = cl > 1 ? 1 : 0;
+            CU(ctx, cudaLaunchKernelEx(&cfg, kernel_for((flags & GPROT_EXACT_KERNEL) != 0, cl), prm));
+        }
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaEventRecord(ctx->ev1, st));
         ctx->launches++;
@@ -411,6 +487,16 @@ int gprot_last_kernel_ms(gprot_ctx* ctx, float* ms) {
 }
 
 int64_t gprot_launch_count(const gprot_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gprot_set_cluster(gprot_ctx* ctx, int ctas_per_problem) {
+    if (!ctx) return fail(nullptr, "null context");
+    if (ctas_per_problem != 0 && ctas_per_problem != 1 && ctas_per_problem != 2 && ctas_per_problem != 4 && ctas_per_problem != 8)
+        return fail(ctx, "ctas_per_problem must be 0 (auto), 1, 2, 4 or 8");
+    ctx->force_cluster = ctas_per_problem;
+    return 0;
+}
+
+int gprot_last_cluster(const gprot_ctx* ctx) { return ctx ? ctx->last_cluster : 0; }
 
 int gprot_measure_dmma_peak(gprot_ctx* ctx, double* tflops, double* sm_clock_mhz) {
     if (!ctx || !tflops) return fail(ctx, "bad arguments");

@@ -140,6 +140,13 @@ class GPEngine(object):
         self._check(self._lib.gprot_last_kernel_ms(self._ctx, byref(ms)))
         return ms.value
 
+    def set_cluster(self, ctas_per_problem=0):
+        """CTAs per problem: 0 = chosen per launch, or 1 / 2 / 4 / 8 (results are bitwise identical)."""
+        self._check(self._lib.gprot_set_cluster(self._ctx, int(ctas_per_problem)))
+
+    def last_cluster(self):
+        return int(self._lib.gprot_last_cluster(self._ctx))
+
     def launch_count(self):
         return int(self._lib.gprot_launch_count(self._ctx))
 

@@ -78,6 +78,13 @@ int gprot_lnpost_batch(gprot_ctx *ctx, int64_t B, const double *theta, const int
 
 int gprot_sync(gprot_ctx *ctx);
 
+/* CTAs per problem.  A launch with fewer problems than SMs (32 problems per GPU for the
+ * N=8192 stress at 8 GPUs; one emcee3 half-ensemble of a single star, gprot/fit.py:98) spreads each problem over a
+ * thread-block cluster of 2, 4 or 8 CTAs.  0 (default) chooses per launch from the batch size; results are bitwise
+ * identical for every setting.  gprot_last_cluster reports what the last launch used. */
+int gprot_set_cluster(gprot_ctx *ctx, int ctas_per_problem);
+int gprot_last_cluster(const gprot_ctx *ctx);
+
 /* Measurement hooks (bench.py): device time of the last likelihood launch, CUDA events on the
  * launching stream; number of kernels launched by this context so far; FP64 tensor (DMMA) peak
  * of this device measured by a register-resident mma.sync.m8n8k4.f64 loop. */

@@ -247,3 +247,54 @@ def test_device_buffers_and_stream(engine):
         engine.lnlike_batch_device(dth.data_ptr(), 32, dout.data_ptr(), lc_id=lc, stream=st.cuda_stream)
     st.synchronize()
     assert np.array_equal(dout.cpu().numpy(), host)
+
+
+@pytest.mark.parametrize("n,chunksize", [(1000, None), (640, None), (1500, 400), (130, None)])
+def test_cluster_variants_are_bitwise_identical(engine, n, chunksize):
+    """a launch with fewer problems than SMs spreads each problem over a thread-block cluster.
+    Every cluster size runs the same arithmetic in the same order, so the outputs must be bit-for-bit those of the
+    one-CTA kernel (and therefore within tolerance of the oracle)."""
+    t, y, yerr, truth = synthetic_lightcurve(100 + n, n, kind="harmonic")
+    engine.unregister_all()
+    chunks = o.split_chunks(n, chunksize)
+    lc = engine.register_lc(t, y, yerr, chunks=chunks)
+    th = o.sample_from_prior(9, seed=n)
+    th[0] = truth
+    th[1, 4] = 50.0          # exp(50) d period against exp(2..20) d^2: still finite; th[2]: non-finite scale -> -inf
+    th[2, 0] = 800.0
+    try:
+        engine.set_cluster(1)
+        base = engine.lnlike_batch(th, lc_id=lc)
+        assert engine.last_cluster() == 1
+        ref = np.array([o.lnlike(x, t, y, yerr, chunks) for x in th])
+        m = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(base), m)
+        assert np.all(np.abs(base[m] - ref[m]) <= 1e-8 * np.abs(ref[m]))
+        for cl in (2, 4, 8):
+            engine.set_cluster(cl)
+            for exact in (False, True):
+                engine.set_cluster(1)
+                b1 = engine.lnlike_batch(th, lc_id=lc, exact=exact)
+                engine.set_cluster(cl)
+                got = engine.lnlike_batch(th, lc_id=lc, exact=exact)
+                assert engine.last_cluster() == cl
+                assert np.array_equal(got, b1), (cl, exact, got, b1)
+        engine.set_cluster(0)
+        got = engine.lnlike_batch(th, lc_id=lc)
+        assert np.array_equal(got, base)
+    finally:
+        engine.set_cluster(0)
+
+
+def test_cluster_auto_choice(engine):
+    """Small batches of large problems pick a cluster; batches that fill the GPU stay at one CTA per problem."""
+    t, y, yerr, _ = synthetic_lightcurve(5, 1536, kind="harmonic")
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    engine.set_cluster(0)
+    th = o.sample_from_prior(300, seed=3)
+    small = engine.lnlike_batch(th[:16], lc_id=lc)
+    assert engine.last_cluster() > 1
+    big = engine.lnlike_batch(th, lc_id=lc)
+    assert engine.last_cluster() == 1
+    assert np.array_equal(small, big[:16])
