@@ -24,6 +24,12 @@
 #include <math.h>
 #include <float.h>
 
+#ifndef PIVOT_VARIANT
+#define PIVOT_VARIANT 1
+#endif
+#ifndef ROWS_VARIANT
+#define ROWS_VARIANT 1
+#endif
 namespace gprot {
 
 constexpr int BS = 128;           // block edge
@@ -49,10 +55,10 @@ struct Smem {
     double yj[BS];                // ytilde_J
     double dinv[BS];              // 1 / diag(L_JJ)
     double wt[128];               // inverse of the current / next 8 x 8 diagonal tile (double buffered)
-    double lpart[4];              // per-warp partial sums of log diag(L_JJ)
+    double lpart[16];             // per-warp partial sums of log diag(L_JJ)
     double etab[64];              // 2^(j/64)
     Hyp hyp;
-    double qpart[4];              // per-warp partial sums of z_J^2 (fixed-order reduction: deterministic)
+    double qpart[16];             // per-warp partial sums of z_J^2 (fixed-order reduction: deterministic)
     unsigned long long full[STAGES];
     unsigned long long empty[STAGES];
     int prob;
@@ -141,6 +147,11 @@ __device__ __forceinline__ int frag_off(int r, int kk) {   // r in [0,128), kk i
     return (r >> 3) * 128 + ((kk >> 3) & 1) * 64 + (((r & 7) << 2) + (kk & 3)) * 2 + ((kk >> 2) & 1);
 }
 __device__ __forceinline__ int w_slab_off(int s) { return 128 * s * (17 - s); }   // slab s keeps row groups 2s..15
+// position of W[c][m] (c >= 16 * (m / 16)) in the packed lower triangle sm.W: k-slab m/16, row group c/8
+__device__ __forceinline__ int w_off(int c, int m) {
+    const int s = m >> 4;
+    return w_slab_off(s) + ((c >> 3) - 2 * s) * 128 + ((m >> 3) & 1) * 64 + (((c & 7) << 2) + (m & 3)) * 2 + ((m >> 2) & 1);
+}
 
 // Store a warp's 32 x 32 C-fragment tile (acc[mi][ni][e] at row 8mi+g, col 8ni+2q+e) into a fragment-major
 // block at tile origin (row0, col0), optionally negated.  Lanes q and q^2 hold neighbouring doubles of the
@@ -354,6 +365,7 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
 // (A register-resident variant without shuffles is faster in isolation -- 1.5k vs 2.1k cycles -- but needs ~110
 // registers on top of the kernel's live state and spills under the 128-register cap of a 512-thread CTA.)
 // Results: L_pp (lower, in M), W_pp^T (strict upper, in M), W_pp (sm.wt[buf], zero above the diagonal), 1/diag (sm.dinv).
+template <bool TO_W = false>
 __device__ __forceinline__ void tile8_factor(Smem& sm, int p, int buf, int lane) {
     double* Mp = sm.regionA + (8 * p) * LDM + 8 * p;
     const int a = lane & 7;
@@ -397,10 +409,66 @@ __device__ __forceinline__ void tile8_factor(Smem& sm, int p, int buf, int lane)
         for (int c = 0; c < 8; c++) {
             const double w = (c <= a) ? inv[c] : 0.0;
             wt[a * 8 + c] = w;                              // W_pp[a][c], zeros above the diagonal
-            if (c < a) Mp[c * LDM + a] = w;                 // strict upper of the tile: W_pp^T
             if (c == a) sm.dinv[8 * p + a] = w;
-            if (c <= a) Mp[a * LDM + c] = row[c];           // L_pp
+            if (TO_W) sm.W[w_off(8 * p + a, 8 * p + c)] = w;   // final position in the B-operand layout
+            else {
+                if (c < a) Mp[c * LDM + a] = w;             // strict upper of the tile: W_pp^T
+                if (c <= a) Mp[a * LDM + c] = row[c];       // L_pp
+            }
         }
+    }
+    if (bad && lane == 0) sm.fail = 1;
+}
+
+// Pivot-tile factorisation without shuffles: every lane of the pivot warp holds the whole lower triangle and runs the
+// same elimination (the dependent chain is rsqrt -> scale -> one DFMA per pivot); lane b < 8 then forms column b of
+// the inverse by forward substitution.  Needs ~100 registers, which only the pivot warp's own loop can afford.
+// Same outputs as tile8_factor<true>: W_pp (sm.wt[buf] and its place in sm.W), 1/diag (sm.dinv).
+__device__ __forceinline__ void tile8_factor_all(Smem& sm, int p, int buf, int lane) {
+    const double* Mp = sm.regionA + (8 * p) * LDM + 8 * p;
+    double l[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+#pragma unroll
+        for (int b2 = 0; b2 <= a / 2; b2++) {
+            const double2 v = *reinterpret_cast<const double2*>(Mp + a * LDM + 2 * b2);
+            l[a][2 * b2] = v.x;
+            if (2 * b2 + 1 <= a) l[a][2 * b2 + 1] = v.y;
+        }
+    }
+    double rinv[8];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const double d = l[j][j];
+        if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
+        const double ri = rsqrt_pos(d);
+        rinv[j] = ri;
+#pragma unroll
+        for (int a = j + 1; a < 8; a++) l[a][j] *= ri;
+#pragma unroll
+        for (int a = j + 1; a < 8; a++)
+#pragma unroll
+            for (int b = j + 1; b <= a; b++) l[a][b] = fma(-l[a][j], l[b][j], l[a][b]);
+    }
+    // 1/l_jj: rinv is 1/sqrt(d) to ~1 ulp, which is what the in-warp variant stores as well (inv[j] * ri with inv = 1)
+    const int b = lane & 7;
+    double w[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < a; m++) s = fma(l[a][m], w[m], s);
+        w[a] = (a == b) ? rinv[a] : ((a > b) ? -rinv[a] * s : 0.0);
+    }
+    if (lane < 8) {
+        double* wt = sm.wt + 64 * buf;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+            wt[a * 8 + b] = w[a];
+            sm.W[w_off(8 * p + a, 8 * p + b)] = w[a];
+        }
+        sm.dinv[8 * p + b] = w[b];
     }
     if (bad && lane == 0) sm.fail = 1;
 }
@@ -486,6 +554,249 @@ __device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, long l
     }
 }
 
+// ---------------------------------------------------------------- diagonal block, trailing tiles in registers
+// Same elimination as diag_factor (bitwise the same L and W), organised so that the rank-8 updates never touch shared
+// memory: warp R owns tile row R of the workspace (8 rows x 128 columns) and keeps its not-yet-eliminated tiles
+// (R, C), C > p, as DMMA accumulators.  Shared memory only carries the current panel column p (M(R, p), rewritten in
+// place with X(R) = M(R, p) W_pp^T), the next panel column (each warp stores tile (R, p+1) right after updating it) and
+// the 8 x 8 pivot tile.  Per step the block-wide work is two 8-byte fragment loads per tile instead of a 16-byte
+// load + store of every trailing tile (the in-place version was bound by shared-memory bandwidth, not by the DMMA
+// pipe); the critical path is the owner of tile row p+1: one tile update, then the pivot-tile factorisation.
+// Finished tiles of W = L_JJ^{-1} go straight to their B-operand position in sm.W (no conversion pass).
+// rank-8 update of the register tiles C = P+2 .. chi of one tile row with panel column P (a0, a1 = A fragment of -X(R));
+// the tile that becomes the next-but-one panel column (C = P+2) is parked in shared memory right after its update
+template <int P>
+__device__ __forceinline__ void rows_update(double (&rt)[16][2], const double* __restrict__ bcol, double* myrow, double a0,
+                                            double a1, int chi, int q) {
+#if ROWS_VARIANT == 1
+#pragma unroll
+    for (int C = P + 2; C < 16; C++) {
+        if (C <= chi) {
+            const double b0 = bcol[(8 * C) * LDM + q], b1 = bcol[(8 * C) * LDM + q + 4];
+            dmma(rt[C][0], rt[C][1], a0, b0);
+            dmma(rt[C][0], rt[C][1], a1, b1);
+            if (C == P + 2) *reinterpret_cast<double2*>(myrow + 8 * C + 2 * q) = make_double2(rt[C][0], rt[C][1]);
+        }
+    }
+#else
+#pragma unroll
+    for (int C0 = P + 2; C0 < 16; C0 += 4) {
+        double b0[4], b1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int C = C0 + u;
+            if (C < 16 && C <= chi) { b0[u] = bcol[(8 * C) * LDM + q]; b1[u] = bcol[(8 * C) * LDM + q + 4]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int C = C0 + u;
+            if (C < 16 && C <= chi) dmma(rt[C][0], rt[C][1], a0, b0[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int C = C0 + u;
+            if (C < 16 && C <= chi) {
+                dmma(rt[C][0], rt[C][1], a1, b1[u]);
+                if (C == P + 2) *reinterpret_cast<double2*>(myrow + 8 * C + 2 * q) = make_double2(rt[C][0], rt[C][1]);
+            }
+        }
+    }
+#endif
+}
+
+#ifdef DIAG_TS
+__device__ long long g_ts[16][8];
+#define TS(p, k) do { if (lane == 0) g_ts[p][k] = clock64(); } while (0)
+#else
+#define TS(p, k) do { } while (0)
+#endif
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// X = M(R, p) W_pp^T for one tile row, rewritten in place; rows above the pivot (R < p) also deliver the finished
+// tile of W^T to sm.W.  Returns the A fragment of -X.
+__device__ __forceinline__ void panel_scale(Smem& sm, double* row, const double* wt, int R, int p, int g, int q, double& a0, double& a1) {
+    const double x0 = row[q], x1 = row[q + 4];
+    const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
+    double c0 = 0.0, c1 = 0.0;
+    dmma(c0, c1, x0, b0);
+    dmma(c0, c1, x1, b1);
+    __syncwarp();
+    *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
+    if (R < p) {                                               // W[8p + 2q + e][8R + g]
+        sm.W[w_off(8 * p + 2 * q, 8 * R + g)] = c0;
+        sm.W[w_off(8 * p + 2 * q + 1, 8 * R + g)] = c1;
+    }
+    __syncwarp();
+    a0 = -row[q]; a1 = -row[q + 4];
+}
+
+// Warp 0 is the pivot warp: it only factors and inverts the 8 x 8 pivot tiles (and scales tile row 0, which stays in
+// shared memory).  Warps 1..15 own tile rows 1..15.  The two roles are separate loops, so the pivot-tile registers and
+// the row accumulators never coexist; they meet at the two block barriers of every step, and the owner of tile row p+1
+// hands the finished pivot tile to warp 0 through named barrier 1 (then updates row 0 while warp 0 factors).
+// nsteps < 16: rows 8 nsteps .. 127 of the block are identity padding; the sweep stops early and diag_pad_identity
+// fills their part of W.  Ends with a block barrier.
+__device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, int nsteps) {
+    const int g = lane >> 2, q = lane & 3;
+    double* M = sm.regionA;
+    if (warp == 0) {
+#if PIVOT_VARIANT == 1
+        tile8_factor_all(sm, 0, 0, lane);
+#else
+        tile8_factor<true>(sm, 0, 0, lane);
+#endif
+        __syncthreads();
+        for (int p = 0; p < nsteps; p++) {
+            TS(p, 0);
+            if (p >= 1) {
+                double a0, a1;
+                panel_scale(sm, M + g * LDM + 8 * p, sm.wt + 64 * (p & 1), 0, p, g, q, a0, a1);
+            }
+            TS(p, 1);
+            __syncthreads();
+            TS(p, 2);
+            if (p == nsteps - 1) break;
+            named_sync(1, 64);                                 // pivot tile (p+1, p+1) is final
+            TS(p, 3);
+#if PIVOT_VARIANT == 1
+            tile8_factor_all(sm, p + 1, (p + 1) & 1, lane);
+#else
+            tile8_factor<true>(sm, p + 1, (p + 1) & 1, lane);
+#endif
+            TS(p, 4);
+            __syncthreads();
+        }
+        return;
+    }
+    const int R = warp;
+    double* myrow = M + (8 * R + g) * LDM;
+    double rt[16][2];                                          // rt[C] = C fragment of tile (R, C), C >= 2
+#pragma unroll
+    for (int C = 2; C < 16; C++) {
+        if (C <= R) {
+            const double2 v = *reinterpret_cast<const double2*>(myrow + 8 * C + 2 * q);
+            rt[C][0] = v.x; rt[C][1] = v.y;
+        } else { rt[C][0] = 0.0; rt[C][1] = 0.0; }
+    }
+    __syncthreads();
+    for (int p = 0; p < nsteps; p++) {
+        const int P0 = 8 * p;
+        const double* wt = sm.wt + 64 * (p & 1);
+        double a0, a1;                                         // A fragment of -X(R)
+        if (R != p) panel_scale(sm, myrow + P0, wt, R, p, g, q, a0, a1);
+        else { a0 = -wt[q * 8 + g]; a1 = -wt[(q + 4) * 8 + g]; }     // rows of the pivot tile act through W_pp^T
+        __syncthreads();                                       // X(C), C > p, visible to every warp
+        if (p == nsteps - 1) break;
+        const int chi = (R <= p) ? 15 : R;                     // tiles p+1 .. chi of this row take the rank-8 update
+        const double* bcol = M + g * LDM + P0;                 // B fragments: X(C) at bcol + 8 C LDM
+        {                                                      // the next panel column lives in shared memory
+            double2* cp = reinterpret_cast<double2*>(myrow + P0 + 8 + 2 * q);
+            double2 c = *cp;
+            const double b0 = bcol[8 * (p + 1) * LDM + q], b1 = bcol[8 * (p + 1) * LDM + q + 4];
+            dmma(c.x, c.y, a0, b0);
+            dmma(c.x, c.y, a1, b1);
+            *cp = c;
+        }
+        if (R == p + 1) {
+            __syncwarp();
+            __threadfence_block();
+            named_arrive(1, 64);                               // hand the pivot tile to warp 0
+            // tile row 0 (kept in shared memory): tiles (0, C), C = p+1 .. 15
+            double r0, r1;
+            if (p == 0) { r0 = -wt[q * 8 + g]; r1 = -wt[(q + 4) * 8 + g]; }
+            else { r0 = -M[g * LDM + P0 + q]; r1 = -M[g * LDM + P0 + q + 4]; }
+            const double* bp = bcol + 8 * (p + 1) * LDM + q;
+            double* cp = M + g * LDM + P0 + 8 + 2 * q;
+            int C = p + 1;
+            for (; C + 1 <= 15; C += 2, bp += 16 * LDM, cp += 16) {
+                const double b00 = bp[0], b01 = bp[4], b10 = bp[8 * LDM], b11 = bp[8 * LDM + 4];
+                double2 x = *reinterpret_cast<double2*>(cp), y = *reinterpret_cast<double2*>(cp + 8);
+                dmma(x.x, x.y, r0, b00);
+                dmma(y.x, y.y, r0, b10);
+                dmma(x.x, x.y, r1, b01);
+                dmma(y.x, y.y, r1, b11);
+                *reinterpret_cast<double2*>(cp) = x;
+                *reinterpret_cast<double2*>(cp + 8) = y;
+            }
+            if (C <= 15) {
+                const double b00 = bp[0], b01 = bp[4];
+                double2 x = *reinterpret_cast<double2*>(cp);
+                dmma(x.x, x.y, r0, b00);
+                dmma(x.x, x.y, r1, b01);
+                *reinterpret_cast<double2*>(cp) = x;
+            }
+        } else {
+#ifndef NO_SWITCH
+            switch (p) {
+                case 0: rows_update<0>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 1: rows_update<1>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 2: rows_update<2>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 3: rows_update<3>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 4: rows_update<4>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 5: rows_update<5>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 6: rows_update<6>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 7: rows_update<7>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 8: rows_update<8>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 9: rows_update<9>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 10: rows_update<10>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 11: rows_update<11>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 12: rows_update<12>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 13: rows_update<13>(rt, bcol, myrow, a0, a1, chi, q); break;
+                default: break;
+            }
+#endif
+        }
+        __syncthreads();                                       // next panel column and its pivot tile are in place
+    }
+}
+
+// rows c >= c0 of W (and of 1/diag) are those of the identity
+__device__ __forceinline__ void diag_pad_identity(Smem& sm, int c0, int tid) {
+    for (int s = 0; s < 8; s++) {
+        const int cnt = (16 - 2 * s) * 128;
+        double* dst = sm.W + w_slab_off(s);
+        for (int d = tid; d < cnt; d += NT) {
+            const int rgrel = d >> 7, kp = (d >> 6) & 1, ln = (d >> 1) & 31, hh = d & 1;
+            const int c = 8 * (2 * s + rgrel) + (ln >> 2);
+            const int m = 16 * s + 4 * (2 * kp + hh) + (ln & 3);
+            if (c >= c0) dst[d] = (m == c) ? 1.0 : 0.0;
+        }
+    }
+    if (tid >= c0 && tid < BS) sm.dinv[tid] = 1.0;
+}
+
+// z_J = W ytilde_J as a DMMA matrix-vector product (ytilde in column 0 of the B operand), |z_J|^2 and sum log L_rr.
+// Warp w owns rows 8w..8w+7; k runs over the slabs 0..w/2 of sm.W (zeros above the diagonal are stored).
+__device__ __forceinline__ void diag_solve(Smem& sm, int warp, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0;
+    for (int s = 0; s <= (warp >> 1); s++) {
+        const double* base = sm.W + w_slab_off(s) + (warp - 2 * s) * 128 + lane * 2;
+        const double2 f0 = *reinterpret_cast<const double2*>(base);
+        const double2 f1 = *reinterpret_cast<const double2*>(base + 64);
+        const double* yk = sm.yj + 16 * s + q;
+        const double y0 = g == 0 ? yk[0] : 0.0, y1 = g == 0 ? yk[4] : 0.0, y2 = g == 0 ? yk[8] : 0.0, y3 = g == 0 ? yk[12] : 0.0;
+        dmma(za0, za1, f0.x, y0);
+        dmma(zb0, zb1, f0.y, y1);
+        dmma(za0, za1, f1.x, y2);
+        dmma(zb0, zb1, f1.y, y3);
+    }
+    const double z = za0 + zb0;                                // rows 8w+g, column 0: lanes with q == 0
+    double z2 = 0.0, lg = 0.0;
+    if (q == 0) {
+        sm.zs[8 * warp + g] = z;
+        z2 = z * z;
+        lg = -log(sm.dinv[8 * warp + g]);                      // log L_rr (identity padding gives exactly 0)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+        lg += __shfl_xor_sync(0xffffffffu, lg, o);
+    }
+    if (lane == 0) { sm.qpart[warp] = z2; sm.lpart[warp] = lg; }
+}
+
 // ---------------------------------------------------------------- the kernel
 // CL = CTAs per problem.  CL > 1 launches thread-block clusters of CL CTAs that share one problem: every CTA forms the
 // diagonal block of a column (redundantly: same operands, same order, bitwise the same W and z_J -- the CTAs would
@@ -499,7 +810,10 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
     const int wr = warp >> 2, wc = ((warp & 3) - (warp >> 2)) & 3;   // skewed so each scheduler sees every wc
     const int g = lane >> 2, q = lane & 3;
 
-    if (tid < 64) sm.etab[tid] = EXP2_64TH[tid];
+    if (tid < 64) {
+        sm.etab[tid] = EXP2_64TH[tid];
+        for (int sl = 0; sl < 8; sl++) sm.W[w_slab_off(sl) + 64 + tid] = 0.0;   // tiles above the diagonal: never written again
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&sm.full[s], 1);
@@ -613,55 +927,26 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 }
                 __syncthreads();
                 TICK(3);
-#ifdef GPROT_TIMING
-                diag_factor(sm, warp, lane, tim_, tlast_);         // ends with __syncthreads
-#else
-                { long long dummy_ = 0; diag_factor(sm, warp, lane, nullptr, dummy_); }
-#endif
-                TICK(4);
-                if (sm.fail) { failed = true; break; }
-                // W -> B-operand fragments (zeros above the diagonal of each 16 x 16 corner), z_J = W ytilde_J
                 {
-                    const double* M = sm.regionA;
-                    for (int s = 0; s < 8; s++) {
-                        const int cnt = (16 - 2 * s) * 128;
-                        double* dst = sm.W + w_slab_off(s);
-                        for (int d = tid; d < cnt; d += NT) {
-                            const int rgrel = d >> 7, kp = (d >> 6) & 1, ln = (d >> 1) & 31, hh = d & 1;
-                            const int c = 8 * (2 * s + rgrel) + (ln >> 2);
-                            const int m = 16 * s + 4 * (2 * kp + hh) + (ln & 3);
-                            dst[d] = (m < c) ? M[m * LDM + c] : ((m == c) ? sm.dinv[c] : 0.0);
-                        }
-                    }
-                    if (tid < BS) {
-                        const int r = tid;
-                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                        int m = 0;
-                        for (; m + 3 < r; m += 4) {
-                            s0 = fma(M[(m + 0) * LDM + r], sm.yj[m + 0], s0);
-                            s1 = fma(M[(m + 1) * LDM + r], sm.yj[m + 1], s1);
-                            s2 = fma(M[(m + 2) * LDM + r], sm.yj[m + 2], s2);
-                            s3 = fma(M[(m + 3) * LDM + r], sm.yj[m + 3], s3);
-                        }
-                        for (; m < r; m++) s0 = fma(M[m * LDM + r], sm.yj[m], s0);
-                        const double z = ((s0 + s1) + (s2 + s3)) + sm.dinv[r] * sm.yj[r];
-                        sm.zs[r] = z;
-                        double z2 = z * z;
-                        double lg = -log(sm.dinv[r]);               // log L_rr (identity padding gives exactly 0)
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            z2 += __shfl_xor_sync(0xffffffffu, z2, o);
-                            lg += __shfl_xor_sync(0xffffffffu, lg, o);
-                        }
-                        if (lane == 0) { sm.qpart[warp] = z2; sm.lpart[warp] = lg; }
+                    const int nreal = min(BS, n - J * BS);          // the rest of the block is identity padding
+                    const int nsteps = (nreal + 7) >> 3;
+                    diag_factor_rows(sm, warp, lane, nsteps);       // ends with __syncthreads
+                    if (nsteps < 16) {
+                        diag_pad_identity(sm, 8 * nsteps, tid);
+                        __syncthreads();
                     }
                 }
+                TICK(4);
+                if (sm.fail) { failed = true; break; }
+                diag_solve(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
                 fence_async();
                 __syncthreads();
                 TICK(5);
                 if (tid == 0) {
-                    quad += (sm.qpart[0] + sm.qpart[1]) + (sm.qpart[2] + sm.qpart[3]);
-                    logdet += (sm.lpart[0] + sm.lpart[1]) + (sm.lpart[2] + sm.lpart[3]);
+                    double qs = 0.0, ls = 0.0;
+                    for (int w = 0; w < 16; w++) { qs += sm.qpart[w]; ls += sm.lpart[w]; }    // fixed order
+                    quad += qs;
+                    logdet += ls;
                 }
             }
             // first block row of this column owned by this CTA (rows are dealt round-robin: I mod CL)

@@ -131,6 +131,216 @@ __global__ void __launch_bounds__(512, 1) k_diag(long long* out, double* sink, i
     if (threadIdx.x == 0) { out[0] = first; out[1] = tot / (reps - 1); sink[0] = sm.dinv[77] + sm.regionA[5 * LDM + 100] + sm.fail; }
 }
 
+// ---- candidate: row-owned rank-8 updates (no per-task index arithmetic, A fragment loaded once per row)
+template <int V>
+__device__ __forceinline__ void diag_factor2(Smem& sm, int warp, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    double* M = sm.regionA;
+    if (warp == 0) { if (V == 0) tile8_factor(sm, 0, 0, lane); else tile8_factor_redundant(sm, 0, 0, lane); }
+    __syncthreads();
+    for (int p = 0; p < 16; p++) {
+        const int P0 = 8 * p;
+        if (warp != p) {
+            const double* wt = sm.wt + 64 * (p & 1);
+            double* row = M + (8 * warp + g) * LDM + P0;
+            const double a0 = row[q], a1 = row[q + 4];
+            const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
+            double c0 = 0.0, c1 = 0.0;
+            dmma(c0, c1, a0, b0);
+            dmma(c0, c1, a1, b1);
+            __syncwarp();
+            *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
+        }
+        __syncthreads();
+        if (p == 15) break;
+        if (warp == 0) {
+            tile8_update(sm, p, p + 1, p + 1, g, q);
+            __syncwarp();
+            if (V == 0) tile8_factor(sm, p + 1, (p + 1) & 1, lane); else tile8_factor_redundant(sm, p + 1, (p + 1) & 1, lane);
+        } else {
+            // worker `warp` owns tile row `warp`; the worker whose only tile is the look-ahead tile takes row 0
+            const int R = (warp == p + 1) ? 0 : warp;
+            const int c0 = p + 1, c1 = (R <= p) ? 15 : R;          // columns c0..c1
+            double a0, a1;
+            if (R == p) {
+                const double* wt = sm.wt + 64 * (p & 1);
+                a0 = -wt[q * 8 + g]; a1 = -wt[(q + 4) * 8 + g];
+            } else {
+                const double* ar = M + (8 * R + g) * LDM + P0;
+                a0 = -ar[q]; a1 = -ar[q + 4];
+            }
+            const double* bp = M + (8 * c0 + g) * LDM + P0 + q;
+            double* cp = M + (8 * R + g) * LDM + 8 * c0 + 2 * q;
+            int C = c0;
+            for (; C + 1 <= c1; C += 2, bp += 16 * LDM, cp += 16) {
+                const double b00 = bp[0], b01 = bp[4], b10 = bp[8 * LDM], b11 = bp[8 * LDM + 4];
+                double2 x = *reinterpret_cast<double2*>(cp), y = *reinterpret_cast<double2*>(cp + 8);
+                dmma(x.x, x.y, a0, b00);
+                dmma(y.x, y.y, a0, b10);
+                dmma(x.x, x.y, a1, b01);
+                dmma(y.x, y.y, a1, b11);
+                *reinterpret_cast<double2*>(cp) = x;
+                *reinterpret_cast<double2*>(cp + 8) = y;
+            }
+            if (C <= c1) {
+                const double b00 = bp[0], b01 = bp[4];
+                double2 x = *reinterpret_cast<double2*>(cp);
+                dmma(x.x, x.y, a0, b00);
+                dmma(x.x, x.y, a1, b01);
+                *reinterpret_cast<double2*>(cp) = x;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(512, 1) k_diag2(long long* out, double* sink, double* dump, int reps) {
+    extern __shared__ __align__(128) unsigned char raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long tot = 0;
+    for (int rep = 0; rep < reps; rep++) {
+        for (int i = threadIdx.x; i < 128 * 128; i += 512) {
+            int a = i / 128, b = i % 128;
+            sm.regionA[a * LDM + b] = (a >= b) ? ((a == b ? 4.0 : 0.0) + exp(-0.01 * (a - b) * (a - b)) + rep * 1e-3 * (a == b)) * 1e-6 : 0.0;
+        }
+        __syncthreads();
+        long long t0 = clock64();
+        if (V < 0) { long long dummy = 0; diag_factor(sm, warp, lane, nullptr, dummy); }
+        else diag_factor2<(V < 0 ? 0 : V)>(sm, warp, lane);
+        long long t1 = clock64();
+        if (rep > 0) tot += t1 - t0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * 128; i += 512) dump[i] = sm.regionA[(i / 128) * LDM + i % 128];
+    if (threadIdx.x < 128) dump[128 * 128 + threadIdx.x] = sm.dinv[threadIdx.x];
+    if (threadIdx.x == 0) { out[0] = tot / (reps - 1); sink[0] = sm.dinv[77] + sm.fail; }
+}
+
+// ---- rows-in-registers variant (gp_kernel.cuh diag_factor_rows + diag_solve) against the in-place sweep + conversion
+template <int V>
+__global__ void __launch_bounds__(512, 1) k_diag3(long long* out, double* dump, int reps) {
+    extern __shared__ __align__(128) unsigned char raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(raw);
+    const int tid = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long tot = 0;
+    if (tid < 64) for (int sl = 0; sl < 8; sl++) sm.W[w_slab_off(sl) + 64 + tid] = 0.0;
+    for (int rep = 0; rep < reps; rep++) {
+        for (int i = threadIdx.x; i < 128 * 128; i += 512) {
+            int a = i / 128, b = i % 128;
+            sm.regionA[a * LDM + b] = (a >= b) ? ((a == b ? 4.0 : 0.0) + exp(-0.01 * (a - b) * (a - b)) + rep * 1e-3 * (a == b)) * 1e-6 : 0.0;
+        }
+        if (tid < 128) sm.yj[tid] = sin(0.37 * tid) * 1e-3;
+        __syncthreads();
+        long long t0 = clock64();
+        if (V == 0) {
+            long long dummy = 0;
+            diag_factor(sm, warp, lane, nullptr, dummy);
+            const double* M = sm.regionA;
+            for (int s = 0; s < 8; s++) {
+                const int cnt = (16 - 2 * s) * 128;
+                double* dst = sm.W + w_slab_off(s);
+                for (int d = tid; d < cnt; d += NT) {
+                    const int rgrel = d >> 7, kp = (d >> 6) & 1, ln = (d >> 1) & 31, hh = d & 1;
+                    const int c = 8 * (2 * s + rgrel) + (ln >> 2);
+                    const int m = 16 * s + 4 * (2 * kp + hh) + (ln & 3);
+                    dst[d] = (m < c) ? M[m * LDM + c] : ((m == c) ? sm.dinv[c] : 0.0);
+                }
+            }
+            if (tid < BS) {
+                const int r = tid;
+                double s0 = 0.0;
+                for (int m = 0; m < r; m++) s0 = fma(M[m * LDM + r], sm.yj[m], s0);
+                sm.zs[r] = s0 + sm.dinv[r] * sm.yj[r];
+            }
+            __syncthreads();
+        } else {
+            diag_factor_rows(sm, warp, lane, 16);
+            diag_solve(sm, warp, lane);
+            __syncthreads();
+        }
+        long long t1 = clock64();
+        if (rep > 0) tot += t1 - t0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W_DOUBLES; i += 512) dump[i] = sm.W[i];
+    if (threadIdx.x < 128) { dump[W_DOUBLES + threadIdx.x] = sm.dinv[threadIdx.x]; dump[W_DOUBLES + 128 + threadIdx.x] = sm.zs[threadIdx.x]; }
+    if (threadIdx.x == 0) { out[0] = tot / (reps - 1); out[1] = sm.fail; }
+}
+
+// diag_factor with per-step timestamps: warp 0 {step start, after (ii)+barrier, after its tile update, after tile8},
+// other warps {end of their (iii) tasks} -> where the 4.2k cycles per step go
+__global__ void __launch_bounds__(512, 1) k_diag_timed(long long* out, double* sink) {
+    extern __shared__ __align__(128) unsigned char raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    __shared__ long long ts[16][20];
+    for (int rep = 0; rep < 3; rep++) {
+        for (int i = threadIdx.x; i < 128 * 128; i += 512) {
+            int a = i / 128, b = i % 128;
+            sm.regionA[a * LDM + b] = (a >= b) ? ((a == b ? 4.0 : 0.0) + exp(-0.01 * (a - b) * (a - b)) + rep * 1e-3 * (a == b)) * 1e-6 : 0.0;
+        }
+        __syncthreads();
+        double* M = sm.regionA;
+        const long long t00 = clock64();
+        if (warp == 0) tile8_factor(sm, 0, 0, lane);
+        __syncthreads();
+        for (int p = 0; p < 16; p++) {
+            const int P0 = 8 * p;
+            if (lane == 0) ts[p][warp == 0 ? 0 : 4] = clock64() - t00;
+            if (warp != p) {
+                const double* wt = sm.wt + 64 * (p & 1);
+                double* row = M + (8 * warp + g) * LDM + P0;
+                const double a0 = row[q], a1 = row[q + 4];
+                const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
+                double c0 = 0.0, c1 = 0.0;
+                dmma(c0, c1, a0, b0);
+                dmma(c0, c1, a1, b1);
+                __syncwarp();
+                *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
+            }
+            if (lane == 0 && warp == 0) ts[p][5] = clock64() - t00;
+            __syncthreads();
+            if (lane == 0 && warp == 0) ts[p][1] = clock64() - t00;
+            if (p == 15) break;
+            const int ncol = 15 - p;
+            const int nrect = (p + 1) * ncol;
+            const int ntask = nrect + ncol * (ncol + 1) / 2;
+            if (warp == 0) {
+                tile8_update(sm, p, p + 1, p + 1, g, q);
+                __syncwarp();
+                if (lane == 0) ts[p][2] = clock64() - t00;
+                tile8_factor(sm, p + 1, (p + 1) & 1, lane);
+                if (lane == 0) ts[p][3] = clock64() - t00;
+            } else {
+                for (int task = warp - 1; task < ntask - 1; task += 15) {
+                    const int tk = task < nrect ? task : task + 1;
+                    int R, C;
+                    if (tk < nrect) { R = tk / ncol; C = p + 1 + tk % ncol; }
+                    else {
+                        const int u = tk - nrect;
+                        int i = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
+                        while ((i + 1) * (i + 2) / 2 <= u) i++;
+                        while (i * (i + 1) / 2 > u) i--;
+                        R = p + 1 + i; C = p + 1 + (u - i * (i + 1) / 2);
+                    }
+                    tile8_update(sm, p, R, C, g, q);
+                }
+                if (lane == 0 && warp == 1) ts[p][6] = clock64() - t00;
+                if (lane == 0 && warp == 15) ts[p][7] = clock64() - t00;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < 16; p++) for (int k = 0; k < 8; k++) out[p * 8 + k] = ts[p][k];
+        sink[0] = sm.dinv[77] + sm.regionA[5 * LDM + 100] + sm.fail;
+    }
+}
+
 int main() {
     long long* out; double* sink;
     cudaMalloc(&out, 64 * 8); cudaMalloc(&sink, 64);
@@ -146,10 +356,57 @@ int main() {
     k_tile8_cta<0><<<148, 512, sizeof(Smem)>>>(out + 24, sink + 4);
     cudaFuncSetAttribute(k_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     k_diag<<<1, 512, sizeof(Smem)>>>(out + 32, sink + 6, 20);
+    long long* out2; cudaMalloc(&out2, 128 * 8);
+    cudaFuncSetAttribute(k_diag_timed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    k_diag_timed<<<1, 512, sizeof(Smem)>>>(out2, sink + 7);
+    long long h2[128];
+    {
+        double* dump; cudaMalloc(&dump, 3 * (128 * 129) * 8);
+        long long* o3; cudaMalloc(&o3, 3 * 8);
+        cudaFuncSetAttribute(k_diag2<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        cudaFuncSetAttribute(k_diag2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        cudaFuncSetAttribute(k_diag2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        k_diag2<-1><<<1, 512, sizeof(Smem)>>>(o3, sink + 7, dump, 20);
+        k_diag2<0><<<1, 512, sizeof(Smem)>>>(o3 + 1, sink + 7, dump + 128 * 129, 20);
+        k_diag2<1><<<1, 512, sizeof(Smem)>>>(o3 + 2, sink + 7, dump + 2 * 128 * 129, 20);
+        cudaError_t e3 = cudaDeviceSynchronize();
+        static double hd[3 * 128 * 129]; long long ho[3];
+        cudaMemcpy(hd, dump, sizeof(hd), cudaMemcpyDeviceToHost); cudaMemcpy(ho, o3, 24, cudaMemcpyDeviceToHost);
+        double d1 = 0, d2 = 0, mx = 0;
+        for (int i = 0; i < 128 * 129; i++) { d1 = fmax(d1, fabs(hd[i] - hd[128 * 129 + i])); d2 = fmax(d2, fabs(hd[i] - hd[2 * 128 * 129 + i])); mx = fmax(mx, fabs(hd[i])); }
+        printf("diag2 status %s: baseline %lld cycles, row-owned %lld cycles (max abs diff %g), row-owned + redundant tile8 %lld cycles (diff %g; max |entry| %g)\n",
+               cudaGetErrorString(e3), ho[0], ho[1], d1, ho[2], d2, mx);
+    }
+    {
+        const int ND = W_DOUBLES + 256;
+        double* dump; cudaMalloc(&dump, 2 * ND * 8);
+        long long* o3; cudaMalloc(&o3, 4 * 8);
+        cudaFuncSetAttribute(k_diag3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        cudaFuncSetAttribute(k_diag3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        k_diag3<0><<<1, 512, sizeof(Smem)>>>(o3, dump, 20);
+        k_diag3<1><<<1, 512, sizeof(Smem)>>>(o3 + 2, dump + ND, 20);
+        cudaError_t e3 = cudaDeviceSynchronize();
+        static double hd[2 * (W_DOUBLES + 256)]; long long ho[4];
+        cudaMemcpy(hd, dump, sizeof(hd), cudaMemcpyDeviceToHost); cudaMemcpy(ho, o3, 32, cudaMemcpyDeviceToHost);
+        double dW = 0, dd = 0, dz = 0, mW = 0, mz = 0; int nbad = 0;
+        for (int i = 0; i < W_DOUBLES; i++) { double d = fabs(hd[i] - hd[ND + i]); if (d > 0) nbad++; dW = fmax(dW, d); mW = fmax(mW, fabs(hd[i])); }
+        for (int i = 0; i < 128; i++) { dd = fmax(dd, fabs(hd[W_DOUBLES + i] - hd[ND + W_DOUBLES + i])); dz = fmax(dz, fabs(hd[W_DOUBLES + 128 + i] - hd[ND + W_DOUBLES + 128 + i])); mz = fmax(mz, fabs(hd[W_DOUBLES + 128 + i])); }
+        printf("diag3 status %s: in-place sweep + conversion + z %lld cycles; rows-in-registers + DMMA z %lld cycles; fail %lld %lld\n", cudaGetErrorString(e3), ho[0], ho[2], ho[1], ho[3]);
+#ifdef DIAG_TS
+        { long long ts[16][8]; cudaMemcpyFromSymbol(ts, gprot::g_ts, sizeof(ts));
+          printf("pivot warp: step start | (ii) row 0 done | barrier 2 passed | pivot tile handed over | tile8 done | (next start)\n");
+          for (int p = 0; p < 15; p++) printf("%2d: %6lld %6lld %6lld %6lld %6lld   step %lld\n", p, 0LL, ts[p][1]-ts[p][0], ts[p][2]-ts[p][0], ts[p][3]-ts[p][0], ts[p][4]-ts[p][0], ts[p+1][0]-ts[p][0]); }
+#endif
+        printf("   W: %d entries differ, max abs diff %g (max |W| %g); dinv diff %g; z diff %g (max |z| %g)\n", nbad, dW, mW, dd, dz, mz);
+    }
     long long h[64]; double hs[8];
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, out, 64 * 8, cudaMemcpyDeviceToHost); cudaMemcpy(hs, sink, 64, cudaMemcpyDeviceToHost);
     printf("status %s\n", cudaGetErrorString(e));
+    cudaMemcpy(h2, out2, 128 * 8, cudaMemcpyDeviceToHost);
+    printf("step: start | w0 (ii) done | barrier passed | w0 update done | w0 tile8 done | w1 tasks done | w15 tasks done\n");
+    for (int p = 0; p < 16; p++)
+        printf("%2d: %7lld %7lld %7lld %7lld %7lld %7lld %7lld\n", p, h2[p * 8 + 0], h2[p * 8 + 5], h2[p * 8 + 1], h2[p * 8 + 2], h2[p * 8 + 3], h2[p * 8 + 6], h2[p * 8 + 7]);
     printf("chain per op: DFMA %.1f  SHFL(double) %.1f  MUFU.RSQ64H+DADD %.1f  DFMA+FSEL %.1f  rsqrt_pos+DADD %.1f cycles\n",
            h[8] / 1000.0, h[9] / 1000.0, h[10] / 1000.0, h[11] / 1000.0, h[12] / 1000.0);
     printf("tile8 lane-distributed: %lld cycles   redundant: %lld cycles   (sinks %g %g)\n", h[0], h[1], hs[0], hs[1]);
