@@ -57,6 +57,8 @@ struct Smem {
     double wt[128];               // inverse of the current / next 8 x 8 diagonal tile (double buffered)
     double lpart[16];             // per-warp partial sums of log diag(L_JJ)
     double etab[64];              // 2^(j/64)
+    double colv[3 * BS];          // block column J: t, sin, cos of the reduced phase
+    double rowv[3 * BS];          // block row I: the same
     Hyp hyp;
     double qpart[16];             // per-warp partial sums of z_J^2 (fixed-order reduction: deterministic)
     unsigned long long full[STAGES];
@@ -81,7 +83,7 @@ struct Params {
     int* counter;                 // work queue head
     double* lscratch;             // per-slot factor scratch
     size_t lslot_stride;          // doubles
-    double* vscratch;             // per-slot vectors: sin, cos, diag, ytilde (4 * npad_max)
+    double* vscratch;             // per-slot vectors: t (clamped), sin, cos, diag, ytilde (5 * npad_max)
     int npad_max;
     long long* timing;            // [16] per-phase cycle totals of CTA 0 (only written when built with -DGPROT_TIMING)
 };
@@ -201,11 +203,11 @@ __constant__ double EXP2_64TH[64] = {
 };
 
 // exp(x) for finite x <= 0, <= 1 ulp: x = (64 k + j) ln2/64 + r, |r| <= ln2/128, exp = 2^k * T[j] * (1 + p(r)),
-// p of degree 5 in Estrin form (truncation r^6/720 < 3.5e-17).  11 FP64-pipe instructions and a dependent chain of 9,
-// about half of the general-purpose exp(); the synthesis of a tile is a latency chain, so both matter.
-// Arguments below -700 are clamped (exp(-700) ~ 1e-304 is zero against any diagonal this model can have).
+// p of degree 5 in Estrin form (truncation r^6/720 < 3.5e-17).  Arguments below -700 give exactly 0 (exp(-700) ~ 1e-304
+// is zero against any diagonal this model can have); the compare is the only FP64 instruction spent on that, the select
+// is integer work.  (Measured: folding A and G into the exponent and reducing the argument with one FMA saves five
+// FP64 instructions per entry but costs 7x in entry accuracy and buys < 1 % -- the synthesis is not FP64-issue bound.)
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
-    x = fmax(x, -700.0);
     const double MAGIC = 0x1.8p+52;
     const double t = fma(x, 0x1.71547652b82fep+6, MAGIC);          // 64/ln2
     const int ki = __double2loint(t);                               // 64 k + j (two's complement, <= 0)
@@ -218,63 +220,79 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
     const double pp = fma(r2, fma(r2, b, a), r);
     const double tj = tab[ki & 63];
     const double res = fma(tj, pp, tj);
-    return __hiloint2double(__double2hiint(res) + ((ki >> 6) << 20), __double2loint(res));
+    int hi = __double2hiint(res) + ((ki >> 6) << 20);
+    int lo = __double2loint(res);
+    if (!(x >= -700.0)) { hi = 0; lo = 0; }
+    return __hiloint2double(hi, lo);
 }
 
 // ---------------------------------------------------------------- covariance synthesis
 // EXACT: george's operation order, entry by entry (oracle/gp_oracle.py kernel_matrix).
 // fast : sin(pi (ti-tj)/P) = si*cj - ci*sj from per-point phases reduced in double-double, one exp.
+// Returns -K_ij (the accumulators hold -S).
 template <bool EXACT>
-__device__ __forceinline__ double kentry(double ti, double tj, double si, double ci, double sj, double cj, const Hyp& h,
-                                         const double* __restrict__ etab) {
+__device__ __forceinline__ double neg_kentry(double ti, double tj, double si, double ci, double sj, double cj, const Hyp& h,
+                                             const double* __restrict__ etab) {
     const double d = ti - tj;
     if (EXACT) {
         const double r2 = __ddiv_rn(__dmul_rn(d, d), h.L);
         const double s = sin(__ddiv_rn(__dmul_rn(M_PI, d), h.P));
         const double e1 = exp(__dmul_rn(-0.5, r2));
         const double e2 = exp(__dmul_rn(__dmul_rn(-h.G, s), s));
-        return __dmul_rn(__dmul_rn(h.A, e1), e2);
+        return -__dmul_rn(__dmul_rn(h.A, e1), e2);
     } else {
         const double sn = si * cj - ci * sj;
-        return h.A * exp_neg(fma(-h.G * sn, sn, -(d * d) * h.hl), etab);
+        return -h.A * exp_neg(fma(-h.G * sn, sn, -(d * d) * h.hl), etab);
     }
 }
 
-// acc <- -K(I,J) for this warp's 32 x 32 tile.  GENERAL handles the diagonal (white noise + yerr),
-// identity padding beyond n, and coincident time stamps off the diagonal.
+// acc <- -K(I,J) for this warp's 32 x 32 tile, from the per-point values staged in shared memory (sm.rowv: block row,
+// sm.colv: block column).  rl0 / cl0 = first row / column of the warp tile inside the block, row0 / col0 the same in
+// the problem.  GENERAL handles the diagonal (white noise + yerr), identity padding beyond n, and coincident time
+// stamps off the diagonal.
 template <bool EXACT, bool GENERAL>
-__device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], int row0, int col0, int n, const double* __restrict__ t,
-                                           const double* vs, const double* vc,
-                                           const double* vd, const Hyp& h, const double* __restrict__ etab, bool white_off, int lane) {
+__device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], const Smem& sm, int rl0, int cl0, int row0, int col0, int n,
+                                           const double* vd, bool white_off, int lane) {
     const int g = lane >> 2, q = lane & 3;
+    const Hyp& h = sm.hyp;
     double ti[4], si[4], ci[4];
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
-        const int r = row0 + 8 * mi + g;
-        ti[mi] = t[GENERAL ? min(r, n - 1) : r];
-        si[mi] = vs[r];
-        ci[mi] = vc[r];
+        const int r = rl0 + 8 * mi + g;
+        ti[mi] = sm.rowv[r];
+        si[mi] = sm.rowv[BS + r];
+        ci[mi] = sm.rowv[2 * BS + r];
     }
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) {
+        const int cl = cl0 + 8 * ni + 2 * q;
+        const double2 tj2 = *reinterpret_cast<const double2*>(sm.colv + cl);
+        const double2 sj2 = *reinterpret_cast<const double2*>(sm.colv + BS + cl);
+        const double2 cj2 = *reinterpret_cast<const double2*>(sm.colv + 2 * BS + cl);
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int c = col0 + 8 * ni + 2 * q + e;
-            const double tj = t[GENERAL ? min(c, n - 1) : c];
-            const double sj = vs[c], cj = vc[c];
+            const double tj = e ? tj2.y : tj2.x, sj = e ? sj2.y : sj2.x, cj = e ? cj2.y : cj2.x;
 #pragma unroll
             for (int mi = 0; mi < 4; mi++) {
-                double k = kentry<EXACT>(ti[mi], tj, si[mi], ci[mi], sj, cj, h, etab);
+                double nk = neg_kentry<EXACT>(ti[mi], tj, si[mi], ci[mi], sj, cj, h, sm.etab);
                 if (GENERAL) {
-                    const int r = row0 + 8 * mi + g;
+                    const int r = row0 + 8 * mi + g, c = col0 + 8 * ni + 2 * q + e;
                     const double d = ti[mi] - tj;
-                    if (r == c) k = (k + h.S) + vd[r];
-                    else if (white_off && d * d < h.thr) k += h.S;
-                    if (r >= n || c >= n) k = (r == c) ? 1.0 : 0.0;
+                    if (r == c) nk = (nk - h.S) - vd[r];
+                    else if (white_off && d * d < h.thr) nk -= h.S;
+                    if (r >= n || c >= n) nk = (r == c) ? -1.0 : 0.0;
                 }
-                acc[mi][ni][e] = -k;
+                acc[mi][ni][e] = nk;
             }
         }
+    }
+}
+
+// stage the per-point values (t, sin, cos) of one 128-point block into shared memory (threads 0..383, one value each)
+__device__ __forceinline__ void stage_points(double* dst, const double* vt, int npad_max, int blk, int tid) {
+    if (tid < 3 * BS) {
+        const int which = tid >> 7, i = tid & (BS - 1);
+        dst[tid] = vt[(size_t)which * npad_max + blk * BS + i];       // vt | vs | vc
     }
 }
 
@@ -830,10 +848,11 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
     const int crank = CL > 1 ? (int)cluster_rank() : 0;
     const int slot = CL > 1 ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
     double* const lbase = prm.lscratch + (size_t)slot * prm.lslot_stride;
-    double* const vs = prm.vscratch + (size_t)slot * 4 * prm.npad_max;
+    double* const vt = prm.vscratch + (size_t)slot * 5 * prm.npad_max;      // t (clamped to the last real point)
+    double* const vs = vt + prm.npad_max;                                   // sin, cos of the reduced phase
     double* const vc = vs + prm.npad_max;
-    double* const vd = vc + prm.npad_max;
-    double* const yw = vd + prm.npad_max;
+    double* const vd = vc + prm.npad_max;                                   // diagonal noise
+    double* const yw = vd + prm.npad_max;                                   // running right-hand side
 
     for (;;) {
         __syncthreads();
@@ -863,7 +882,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         if (tid == 0) {
             Hyp h;
             h.A = exp(th[0]); h.L = exp(th[1]); h.G = exp(th[2]); h.S = exp(th[3]); h.P = exp(th[4]);
-            h.hl = 0.5 / h.L;
+            h.hl = fmin(0.5 / h.L, DBL_MAX);                 // denormal L: d = 0 keeps exp(0), d != 0 underflows, as in the reference
             h.thr = DBL_EPSILON * h.L;
             sm.hyp = h;
         }
@@ -880,8 +899,8 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         // per-point vectors: phase of t_i / P reduced in double-double, diagonal noise, working copy of y
         for (int i = crank * NT + tid; i < npad; i += CL * NT) {
             double s = 0.0, c = 1.0, dg = 0.0, yy = 0.0;
+            const double ti = t[min(i, n - 1)];
             if (i < n) {
-                const double ti = t[i];
                 const double hi = ti / h.P;
                 const double lo = fma(-hi, h.P, ti) / h.P;      // t/P = hi + lo to ~106 bits
                 const double ph = (hi - rint(hi)) + lo;          // |ph| <= 0.5 (+ tiny): sin^2 is invariant to the dropped integer
@@ -890,7 +909,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 dg = e * e;
                 yy = y[i];
             }
-            vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
+            vt[i] = ti; vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
         }
         if (CL > 1) cluster_sync(); else __syncthreads();
         TICK(0);
@@ -902,11 +921,16 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         for (int J = 0; J < T && !failed; J++) {
             const double* jrow = lbase + (size_t)(J * (J - 1) / 2) * BLKD;   // blocks (J, 0..J-1), contiguous
             const int niter = 8 * J;
+            // first block row of this column owned by this CTA (rows are dealt round-robin: I mod CL)
+            const int I0 = CL > 1 ? J + 1 + ((crank - (J + 1)) % CL + CL) % CL : J + 1;
+            stage_points(sm.colv, vt, prm.npad_max, J, tid);       // per-point values of block J: column side ...
+            stage_points(sm.rowv, vt, prm.npad_max, J, tid);        // ... and row side of the diagonal tile
+            __syncthreads();
             // ================= diagonal block (J, J)
             {
                 const bool active = wr >= wc;
                 if (tid == 0) prologue<true>(sm, it, jrow, jrow, niter);
-                if (active) synth_tile<EXACT, true>(acc, J * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
+                if (active) synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, J * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
                 TICK(1);
                 accumulate<true>(sm, acc, it, jrow, jrow, niter, wr, wc, lane, active);
                 __syncthreads();                                   // all stages consumed: regionA becomes M
@@ -939,6 +963,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 TICK(4);
                 if (sm.fail) { failed = true; break; }
                 diag_solve(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
+                if (I0 < T) stage_points(sm.rowv, vt, prm.npad_max, I0, tid);   // row side of the first block below
                 fence_async();
                 __syncthreads();
                 TICK(5);
@@ -949,14 +974,12 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                     logdet += ls;
                 }
             }
-            // first block row of this column owned by this CTA (rows are dealt round-robin: I mod CL)
-            const int I0 = CL > 1 ? J + 1 + ((crank - (J + 1)) % CL + CL) % CL : J + 1;
             if (tid == 0 && I0 < T) prologue<false>(sm, it, lbase + (size_t)(I0 * (I0 - 1) / 2) * BLKD, jrow, niter);
             // ================= blocks below the diagonal (their first slabs are already in flight)
             for (int I = I0; I < T; I += CL) {
                 const double* irow = lbase + (size_t)(I * (I - 1) / 2) * BLKD;
-                if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
-                else                                synth_tile<EXACT, true>(acc, I * BS + 32 * wr, J * BS + 32 * wc, n, t, vs, vc, vd, h, sm.etab, white_off, lane);
+                if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
+                else                                synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
                 TICK(6);
                 accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, true);
                 __syncthreads();                                   // stages drained: regionA becomes the S_IJ staging block
@@ -1032,6 +1055,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 // stored as each warp finishes: warps with a short triangular product overlap their stores with the
                 // others' DMMAs
                 store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
+                if (I + CL < T) stage_points(sm.rowv, vt, prm.npad_max, I + CL, tid);   // row side of the next block
                 fence_async();
                 __syncthreads();                                   // staging reads done (regionA free again), partials visible
                 TICK(9);

@@ -303,7 +303,7 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
             ctx->d_vscratch = nullptr;
             const int np2 = std::max(npad, ctx->v_npad);
             const int want = std::max(ctx->lslots, ctx->vslots);
-            CU(ctx, cudaMalloc((void**)&ctx->d_vscratch, (size_t)want * 4 * np2 * 8));
+            CU(ctx, cudaMalloc((void**)&ctx->d_vscratch, (size_t)want * 5 * np2 * 8));
             ctx->v_npad = np2;
             ctx->vslots = want;
         }
