@@ -87,3 +87,145 @@ class EnsemblePool(object):
 
     def __exit__(self, *exc):
         self.close()
+
+
+def write_samples(mod, df, resultsdir='results', true_period=None):
+    """gprot/fit.py:24-51.  The reference writes ``results/{name}.h5`` with pandas-HDF keys ``samples``, ``lc``,
+    ``gp_prior`` and ``period_prior``; pandas' HDF writer needs PyTables, which this image lacks, so the same four
+    tables go to HDF when PyTables is importable and otherwise to ``results/{name}.npz`` (arrays under the same
+    keys, column names under ``<key>_columns``).  The corner plot (matplotlib) is not part of this path."""
+    import os
+
+    import pandas as pd
+
+    if not os.path.exists(resultsdir):
+        os.makedirs(resultsdir)
+    prior_df = pd.DataFrame({'mu': mod.gp_prior_mu, 'sigma': mod.gp_prior_sigma})
+    tables = {'samples': df, 'lc': mod.lc.df, 'gp_prior': prior_df}
+    if mod.acf_prior:
+        tables['period_prior'] = pd.DataFrame(mod.period_mixture, columns=['w', 'mu', 'sigma'])
+    try:
+        import tables as _pytables  # noqa: F401
+
+        samplefile = os.path.join(resultsdir, '{}.h5'.format(mod.name))
+        for key, t in tables.items():
+            t.to_hdf(samplefile, key=key)
+    except ImportError:
+        samplefile = os.path.join(resultsdir, '{}.npz'.format(mod.name))
+        out = {}
+        for key, t in tables.items():
+            out[key] = t.values
+            out[key + '_columns'] = np.array(list(t.columns))
+        np.savez(samplefile, **out)
+    print('Samples, light curve, and prior saved to {}.'.format(samplefile))
+    return samplefile
+
+
+def read_samples(samplefile, key='samples'):
+    """Counterpart of ``pd.read_hdf(file, key)`` in the reference's downstream scripts (gprot/summary.py:38-56)."""
+    import pandas as pd
+
+    if samplefile.endswith('.npz'):
+        with np.load(samplefile, allow_pickle=False) as z:
+            return pd.DataFrame(z[key], columns=[str(c) for c in z[key + '_columns']])
+    return pd.read_hdf(samplefile, key)
+
+
+def fit_emcee3(mod, nwalkers=500, verbose=False, nsamples=5000, targetn=6,
+               iter_chunksize=10, pool=None, overwrite=False,
+               maxiter=100, sample_directory='mcmc_chains',
+               nburn=3, mixedmoves=True, resultsdir='results', seed=None, **kwargs):
+    """gprot/fit.py:53-152 with the same arguments and control flow: resume from the stored chain unless
+    ``overwrite``, a 0.4 / 0.4 / 0.2 mixture of KDE, DE(1.0) and DE-snooker moves, blocks of ``iter_chunksize``
+    steps until the chain is ``targetn`` autocorrelation times long, ``nburn`` autocorrelation times discarded,
+    ``nsamples`` random draws written with ``write_samples``.  ``pool`` defaults to ``EnsemblePool``: every
+    half-ensemble proposal set is one device launch (the reference's DefaultPool / schwimmbad pool evaluates one
+    walker per call).  ``seed`` (not in the reference) makes a run reproducible."""
+    import os
+
+    import pandas as pd
+
+    from . import sampler as em
+
+    walker = Emcee3Model(mod)
+    rs = np.random.RandomState(seed)
+
+    if sample_directory is not None:
+        sample_file = os.path.join(sample_directory, '{}.h5'.format(mod.name))
+        if not os.path.exists(sample_directory):
+            os.makedirs(sample_directory)
+        backend = em.HDFBackend(sample_file)
+        try:
+            coords_init = backend.current_coords
+        except (AttributeError, KeyError):
+            coords_init = mod.sample_from_prior(nwalkers, seed=seed)
+    else:
+        backend = em.Backend()
+        coords_init = mod.sample_from_prior(nwalkers, seed=seed)
+
+    if mixedmoves:
+        moves = [(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)]
+    else:
+        moves = em.KDEMove()
+
+    sampler = em.Sampler(moves, backend=backend)
+    if overwrite:
+        sampler.reset()
+        coords_init = mod.sample_from_prior(nwalkers, seed=seed)
+
+    if pool is None:
+        pool = EnsemblePool()
+
+    ensemble = em.Ensemble(walker, coords_init, pool=pool, random=rs)
+
+    def calc_stats(s):
+        tau = s.get_integrated_autocorr_time(c=1)
+        tau_max = tau.max()
+        neff = s.backend.niter / tau_max - nburn
+        if verbose:
+            print("Maximum autocorrelation time: {0}".format(tau_max))
+            print("N_eff: {0}\n".format(neff * nwalkers))
+        return tau_max, neff
+
+    done = False
+    tau_max = 0
+    if not overwrite:
+        try:
+            if verbose:
+                print('Status from previous run:')
+            tau_max, neff = calc_stats(sampler)
+            if neff > targetn:
+                done = True
+        except (em.AutocorrError, KeyError, AttributeError):
+            pass
+
+    chunksize = iter_chunksize
+    for iteration in range(maxiter):
+        if done:
+            break
+        if verbose:
+            print("Iteration {0}...".format(iteration + 1))
+        sampler.run(ensemble, chunksize, progress=verbose)
+        try:
+            tau_max, neff = calc_stats(sampler)
+        except em.AutocorrError:
+            tau_max = 0
+            continue
+        if neff > targetn:
+            done = True
+
+    burnin = int(nburn * tau_max)
+    ntot = nsamples
+    samples = sampler.get_coords(flat=True, discard=burnin)
+    total_samples = len(samples)
+    if ntot > total_samples:
+        ntot = total_samples
+    if verbose:
+        print("Discarding {0} samples for burn-in".format(burnin))
+        print("Randomly choosing {0} samples".format(ntot))
+    inds = rs.choice(total_samples, size=ntot, replace=False)
+    samples = samples[inds]
+
+    df = pd.DataFrame(samples, columns=mod.param_names)
+    write_samples(mod, df, resultsdir=resultsdir)
+    return df

@@ -4,12 +4,24 @@ Mirrors the part of the reference's LightCurve that the likelihood reads (gprot/
 329-342, 375-459): ``x / y / yerr`` arrays, optional random subsampling, and the lazily built
 chunk lists ``x_list / y_list / yerr_list`` (``np.array_split`` into chunks no larger than
 ``chunksize``; ``None`` when ``chunksize is None`` -- the ``--nochunks`` single N x N problem).
-ACF, filtering, quarter splitting, plotting and data download are host pre-processing that runs
-once per star and are out of scope.
+Also the front end gprot-fit needs around it: sigma clipping, ``best_sublc`` /
+``make_best_chunks`` (the ``--clever`` tiered chunks, gprot/lc.py:226-281) and the Aigrain hares-and-hounds text
+loader (gprot/aigrain.py:17-56, 117-127).  ACF, bandpass filtering, quarter tables, plotting and data download are
+host pre-processing that runs once per star and stay out of scope.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
+
+
+def sigma_clip(x, y, yerr, nsigma):
+    """gprot/filter.py:5-10: drop points further than nsigma * (rms about the median) from the median."""
+    med = np.median(y)
+    std = (np.sum((med - y) ** 2) / float(len(y))) ** 0.5
+    m = np.abs(y - med) > (nsigma * std)
+    return x[~m], y[~m], yerr[~m]
 
 
 class LightCurve(object):
@@ -72,8 +84,9 @@ class LightCurve(object):
         if sub is None:
             return
         n = len(self._x)
-        rs = np.random.RandomState(seed)
-        inds = np.sort(rs.choice(n, n // sub, replace=False))
+        if seed is not None:                     # np.random.seed(seed); np.random.choice(...) in the reference
+            np.random.seed(seed)
+        inds = np.sort(np.random.choice(n, n // sub, replace=False))
         self._x, self._y, self._yerr = self._x[inds], self._y[inds], self._yerr[inds]
         self._invalidate()
 
@@ -114,6 +127,65 @@ class LightCurve(object):
             self._make_chunks()
         return self._yerr_list
 
+    # ---- full-resolution arrays and the tiered chunks of gprot-fit --clever
+    @property
+    def x_full(self):
+        return self._x_full
+
+    @property
+    def y_full(self):
+        return self._y_full
+
+    @property
+    def yerr_full(self):
+        return self._yerr_full
+
+    def sigma_clip(self, nsigma):
+        """gprot/lc.py:397-398."""
+        self._x, self._y, self._yerr = sigma_clip(self._x, self._y, self._yerr, nsigma)
+        self._invalidate()
+
+    def best_sublc(self, ndays, npoints=600, chunksize=300, flat_order=3, **kwargs):
+        """New sub-LightCurve over the ``ndays`` window with the largest detrended rms, subsampled to about
+        ``npoints`` points (gprot/lc.py:226-265)."""
+        x_full, y_full = self.x_full, self.y_full
+        N = len(x_full)
+        cadence = np.median(x_full[1:] - x_full[:-1])
+        window = int(ndays / cadence)
+        stepsize = max(window // 50, 1)
+        i1, i2 = 0, window
+        max_std, max_i1, max_i2 = 0, None, None
+        while i2 < N:
+            x, y = x_full[i1:i2].copy(), y_full[i1:i2].copy()
+            x, y, _ = sigma_clip(x, y, y, 5)
+            p = np.polyfit(x, y, flat_order)
+            y -= np.polyval(p, x)
+            std = np.std(y)
+            if std > max_std:
+                max_i1, max_i2, max_std = i1, i2, std
+            i1 += stepsize
+            i2 += stepsize
+        if max_i1 is None:                      # window longer than the light curve: use all of it
+            max_i1, max_i2 = 0, N
+        x, y, yerr = x_full[max_i1:max_i2], y_full[max_i1:max_i2], self.yerr_full[max_i1:max_i2]
+        if 'sub' not in kwargs:
+            kwargs['sub'] = max(window // npoints, 1)
+        return LightCurve(x, y, yerr, chunksize=chunksize, name=self.name + '_{:.0f}d'.format(ndays), **kwargs)
+
+    def make_best_chunks(self, ndays=(800, 200, 50), seed=None, **kwargs):
+        """Chunk lists built from the most variable 800 / 200 / 50 day windows (gprot/lc.py:267-281); the
+        sub-light-curves draw their subsamples from the global NumPy RNG seeded here, as the reference does."""
+        if not hasattr(ndays, '__iter__'):
+            ndays = [ndays]
+        xl, yl, el = [], [], []
+        np.random.seed(seed)
+        for nd in ndays:
+            lc = self.best_sublc(nd, **kwargs)
+            xl += list(lc.x_list)
+            yl += list(lc.y_list)
+            el += list(lc.yerr_list)
+        self._x_list, self._y_list, self._yerr_list = xl, yl, el
+
     @property
     def is_split(self):
         return self.x_list is not None
@@ -123,3 +195,63 @@ class LightCurve(object):
         import pandas as pd
 
         return pd.DataFrame({"x": self.x, "y": self.y, "yerr": self.yerr})
+
+
+class AigrainLightCurve(LightCurve):
+    """Aigrain et al. (2015) hares-and-hounds simulation ``i`` (gprot/aigrain.py:17-56): two-column text file
+    ``<dir>/<subdir>/lightcurve_%04d.txt`` (time, relative flux), ``y - 1``, constant ``yerr = 1e-5``, subsample
+    seeded with the star index, optional range restriction, 5-sigma clip.  ``directory`` defaults to the
+    AIGRAIN_ROTATION environment variable (gprot/config.py:3-4)."""
+    subdir = 'final'
+
+    def __init__(self, i, ndays=None, sub=40, rng=None, nsigma=5, directory=None, **kwargs):
+        self.i = i
+        self.quarters = None
+        if directory is None:
+            directory = os.getenv('AIGRAIN_ROTATION', '../code/simulations/kepler_diffrot_full')
+        self.directory = directory
+        sid = str(int(i)).zfill(4)
+        x, y = np.genfromtxt(os.path.join(directory, self.subdir, "lightcurve_{0}.txt".format(sid))).T
+        yerr = np.ones(len(y)) * 1e-5
+        super(AigrainLightCurve, self).__init__(x, y - 1, yerr, sub=sub, **kwargs)
+        if rng is not None:
+            self.restrict_range(rng)
+        elif ndays is not None:
+            self.restrict_range((0, ndays))
+        if nsigma is not None:
+            self.sigma_clip(nsigma)
+        self._sim_params = None
+
+    @property
+    def name(self):
+        if getattr(self, '_name', None) is None:
+            self._name = str(self.i)
+        return self._name
+
+    @name.setter
+    def name(self, value):
+        self._name = value
+
+    def subsample(self, *args, **kwargs):
+        if 'seed' not in kwargs:
+            kwargs['seed'] = self.i
+        super(AigrainLightCurve, self).subsample(*args, **kwargs)
+
+    def make_best_chunks(self, *args, **kwargs):
+        if 'seed' not in kwargs:
+            kwargs['seed'] = self.i
+        super(AigrainLightCurve, self).make_best_chunks(*args, **kwargs)
+
+    @property
+    def sim_params(self):
+        """Row ``i`` of ``<dir>/par/final_table.txt`` (gprot/aigrain.py:91-95, 117-127)."""
+        if self._sim_params is None:
+            import pandas as pd
+
+            df = pd.read_csv(os.path.join(self.directory, 'par', 'final_table.txt'), sep=r'\s+')
+            self._sim_params = df.iloc[int(self.i)]
+        return self._sim_params
+
+
+class NoiseFreeAigrainLightCurve(AigrainLightCurve):
+    subdir = 'noise_free'

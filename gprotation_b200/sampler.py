@@ -1,0 +1,453 @@
+"""Ensemble sampler with the emcee3 surface that gprot/fit.py uses -- proposals evaluated as ONE batched launch.
+
+The reference drives the likelihood through dfm/emcee3 (unreleased, unpinned; not installable offline --
+SURVEY.md section 8c).  Its call sites (gprot/fit.py:6-7, 11-22, 83-89, 98, 103, 119, 128, 139) use:
+
+    emcee3.Model / State          walker -> log_prior, log_likelihood
+    emcee3.Ensemble(walker, coords, pool=pool)
+    emcee3.moves.KDEMove(), DEMove(1.0), DESnookerMove()   mixed with weights 0.4 / 0.4 / 0.2
+    emcee3.Sampler(moves, backend=...).run(ensemble, n, progress=...)
+    sampler.get_integrated_autocorr_time(c=1), sampler.get_coords(flat=True, discard=...), sampler.reset()
+    emcee3.backends.Backend / HDFBackend (current_coords, niter), emcee3.autocorr.AutocorrError
+    emcee3.pools.DefaultPool
+
+This module restates that surface (same names, argument meaning and error behaviour) following emcee3's published
+algorithms: red-blue ensemble moves (each half of the walkers is updated from the complementary half, Foreman-Mackey
+et al. 2013), differential evolution (ter Braak 2006), the snooker update (ter Braak & Vrugt 2008), a KDE
+independence proposal, and the windowed integrated autocorrelation time.  The one structural difference is the point
+of the whole repository: every proposal set of a half-ensemble is known before any likelihood is needed
+(SURVEY.md section 8a, a11), so ``Ensemble.propose`` hands the *list* of states to ``pool.map`` once and
+``fit.EnsemblePool`` turns it into a single device launch instead of one process call per walker.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .fit import Emcee3Model, EnsemblePool, State
+
+__all__ = ["AutocorrError", "integrated_time", "Backend", "NPZBackend", "HDFBackend", "Ensemble", "Sampler",
+           "StretchMove", "DEMove", "DESnookerMove", "KDEMove", "DefaultPool", "Model", "State"]
+
+Model = Emcee3Model
+
+
+class DefaultPool(object):
+    """emcee3.pools.DefaultPool: serial ``map``.  With an ``Emcee3Model`` walker the states are still evaluated as one
+    batch (the model's ``evaluate_states``) -- per-walker Python calls are what this repository removes."""
+
+    def map(self, func, iterable):
+        if isinstance(func, Emcee3Model) and hasattr(func.mod, "lnpost_batch"):
+            return func.evaluate_states(iterable)
+        return [func(x) for x in iterable]
+
+
+# ------------------------------------------------------------------------------------------ autocorrelation
+class AutocorrError(Exception):
+    """Raised when the chain is too short to estimate the autocorrelation time (emcee3.autocorr.AutocorrError)."""
+
+
+def autocorr_function(x, axis=0):
+    """Normalised autocorrelation function of a (multi-dimensional) time series along ``axis`` (FFT, zero padded)."""
+    x = np.atleast_1d(x)
+    m = [slice(None)] * x.ndim
+    n = int(2 ** np.ceil(np.log2(x.shape[axis]))) * 2
+    f = np.fft.fft(x - np.mean(x, axis=axis, keepdims=True), n=n, axis=axis)
+    m[axis] = slice(0, x.shape[axis])
+    acf = np.fft.ifft(f * np.conjugate(f), axis=axis)[tuple(m)].real
+    m[axis] = 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return acf / np.expand_dims(acf[tuple(m)], axis)
+
+
+def integrated_time(x, low=10, high=None, step=1, c=10, full_output=False, axis=0):
+    """Windowed estimate tau = 1 + 2 sum_{t<M} rho(t) with the smallest window M > c * tau
+    (the estimator gprot/fit.py:103 calls through ``get_integrated_autocorr_time(c=1)``)."""
+    size = 0.5 * x.shape[axis]
+    if int(size) <= low:
+        raise AutocorrError("The chain is too short")
+    if high is None:
+        high = int(size / c)
+    f = autocorr_function(x, axis=axis)
+    if f.ndim == 1:
+        f = f[:, None]
+        axis = 0
+    f = np.moveaxis(f, axis, 0)
+    csum = np.cumsum(f[1:], axis=0)                 # csum[M-2] = sum_{t=1}^{M-1} rho(t)
+    for M in np.arange(low, max(high, low + 1), step).astype(int):
+        tau = 1.0 + 2.0 * csum[M - 2]
+        if np.all(tau > 1.0) and M > c * tau.max():
+            if full_output:
+                return tau, M
+            return tau
+        if c * tau.max() >= size:
+            break
+    raise AutocorrError("The chain is too short to reliably estimate the autocorrelation time")
+
+
+# ------------------------------------------------------------------------------------------ backends
+class Backend(object):
+    """In-memory chain store (emcee3.backends.Backend)."""
+
+    def __init__(self):
+        self._clear()
+
+    def reset(self):
+        self._clear()
+
+    def _clear(self):
+        self.niter = 0
+        self._coords = None
+        self._log_prior = None
+        self._log_likelihood = None
+        self._accepted = None
+        self._size = 0
+
+    def extend(self, n, nwalkers, ndim):
+        if self._coords is None:
+            self._coords = np.empty((n, nwalkers, ndim))
+            self._log_prior = np.empty((n, nwalkers))
+            self._log_likelihood = np.empty((n, nwalkers))
+            self._accepted = np.zeros(nwalkers, dtype=np.int64)
+            self._size = n
+            return
+        if self._coords.shape[1:] != (nwalkers, ndim):
+            raise ValueError("the ensemble shape does not match the stored chain")
+        need = self.niter + n
+        if need > self._size:
+            grow = max(need, 2 * self._size) - self._size
+            self._coords = np.concatenate([self._coords, np.empty((grow, nwalkers, ndim))])
+            self._log_prior = np.concatenate([self._log_prior, np.empty((grow, nwalkers))])
+            self._log_likelihood = np.concatenate([self._log_likelihood, np.empty((grow, nwalkers))])
+            self._size += grow
+
+    def update(self, ensemble):
+        i = self.niter
+        if self._coords is None or i >= self._size:
+            self.extend(max(1, self._size), ensemble.nwalkers, ensemble.ndim)
+        self._coords[i] = ensemble.coords
+        self._log_prior[i] = ensemble.log_prior
+        self._log_likelihood[i] = ensemble.log_likelihood
+        self._accepted += ensemble.acceptance
+        self.niter += 1
+
+    # ---- views
+    def _check(self):
+        if self.niter <= 0 or self._coords is None:
+            raise AttributeError("You need to run the chain first or store the chain using the store keyword argument")
+
+    @property
+    def coords(self):
+        self._check()
+        return self._coords[: self.niter]
+
+    @property
+    def log_prior(self):
+        self._check()
+        return self._log_prior[: self.niter]
+
+    @property
+    def log_likelihood(self):
+        self._check()
+        return self._log_likelihood[: self.niter]
+
+    @property
+    def log_probability(self):
+        return self.log_prior + self.log_likelihood
+
+    @property
+    def acceptance_fraction(self):
+        self._check()
+        return self._accepted / float(self.niter)
+
+    @property
+    def current_coords(self):
+        self._check()
+        return self._coords[self.niter - 1]
+
+    def get_coords(self, flat=False, thin=1, discard=0):
+        v = self.coords[discard + thin - 1 :: thin]
+        return v.reshape(-1, v.shape[-1]) if flat else v
+
+    def get_log_probability(self, flat=False, thin=1, discard=0):
+        v = self.log_probability[discard + thin - 1 :: thin]
+        return v.reshape(-1) if flat else v
+
+    def get_integrated_autocorr_time(self, **kwargs):
+        return integrated_time(np.mean(self.get_coords(), axis=1), **kwargs)
+
+
+class NPZBackend(Backend):
+    """Chain store persisted to ``filename`` (.npz) so a fit can resume from ``current_coords``
+    (gprot/fit.py:69-80 does this with emcee3's HDFBackend; h5py is not installed here, the file layout is the
+    same set of arrays).  ``save()`` is called by the sampler after every ``run``."""
+
+    def __init__(self, filename):
+        self.filename = filename
+        super(NPZBackend, self).__init__()
+        if os.path.exists(filename):
+            with np.load(filename) as z:
+                self._coords = z["coords"].copy()
+                self._log_prior = z["log_prior"].copy()
+                self._log_likelihood = z["log_likelihood"].copy()
+                self._accepted = z["accepted"].copy()
+                self.niter = int(self._coords.shape[0])
+                self._size = self.niter
+
+    def reset(self):
+        self._clear()
+        if os.path.exists(self.filename):
+            os.remove(self.filename)
+
+    def save(self):
+        if self.niter <= 0:
+            return
+        d = os.path.dirname(os.path.abspath(self.filename))
+        if not os.path.exists(d):
+            os.makedirs(d)
+        tmp = self.filename + ".tmp.npz"
+        np.savez(tmp, coords=self.coords, log_prior=self.log_prior, log_likelihood=self.log_likelihood,
+                 accepted=self._accepted)
+        os.replace(tmp, self.filename)
+
+
+def HDFBackend(filename, **kwargs):
+    """emcee3.backends.HDFBackend stand-in: an HDF5-backed store needs h5py, which this image does not have; the
+    chain is kept in the sibling ``.npz`` instead (same arrays, same resume behaviour)."""
+    base, ext = os.path.splitext(filename)
+    return NPZBackend(base + ".npz" if ext in (".h5", ".hdf5", ".hdf") else filename)
+
+
+# ------------------------------------------------------------------------------------------ ensemble
+class Ensemble(object):
+    """The walkers (emcee3.Ensemble): ``model`` maps a State to a State with log_prior / log_likelihood filled in;
+    all states of a proposal set go through ``pool.map`` in ONE call."""
+
+    def __init__(self, model, coords, pool=None, random=None):
+        self.model = model
+        self.pool = DefaultPool() if pool is None else pool
+        self.random = np.random.RandomState() if random is None else random
+        coords = np.atleast_2d(np.asarray(coords, dtype=np.float64))
+        self.walkers = self.propose(coords)
+        self.acceptance = np.ones(len(self.walkers), dtype=bool)
+        if not np.all(np.isfinite(self.log_probability)):
+            raise ValueError("invalid or zero-probability coordinates for at least one walker")
+
+    def propose(self, coords):
+        states = [State(c) for c in np.atleast_2d(coords)]
+        return list(self.pool.map(self.model, states))
+
+    def update(self, walkers, subset=None):
+        """Replace the walkers of ``subset`` (boolean mask) by the accepted proposals."""
+        idx = np.arange(len(self.walkers)) if subset is None else np.flatnonzero(subset)
+        if len(idx) != len(walkers):
+            raise ValueError("subset and proposal sizes differ")
+        for j, w in zip(idx, walkers):
+            self.acceptance[j] = bool(w.accepted)
+            if w.accepted:
+                self.walkers[j] = w
+
+    def __len__(self):
+        return len(self.walkers)
+
+    @property
+    def nwalkers(self):
+        return len(self.walkers)
+
+    @property
+    def ndim(self):
+        return len(self.walkers[0].coords)
+
+    @property
+    def coords(self):
+        return np.stack([w.coords for w in self.walkers])
+
+    @property
+    def log_prior(self):
+        return np.array([w.log_prior for w in self.walkers], dtype=np.float64)
+
+    @property
+    def log_likelihood(self):
+        return np.array([w.log_likelihood for w in self.walkers], dtype=np.float64)
+
+    @property
+    def log_probability(self):
+        return np.array([w.log_probability for w in self.walkers], dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------ moves
+class RedBlueMove(object):
+    """Split the walkers into ``nsplits`` groups; each group is moved using the others as the complementary
+    ensemble, which keeps detailed balance while the whole group is proposed -- and evaluated -- at once."""
+
+    def __init__(self, nsplits=2, randomize_split=False, live_dangerously=False):
+        self.nsplits = int(nsplits)
+        self.randomize_split = randomize_split
+        self.live_dangerously = live_dangerously
+
+    def get_proposal(self, ensemble, s, c):
+        raise NotImplementedError
+
+    def update(self, ensemble):
+        nwalkers, ndim = ensemble.nwalkers, ensemble.ndim
+        if nwalkers < 2 * ndim and not self.live_dangerously:
+            raise RuntimeError("It is unadvisable to use a red-blue move with fewer walkers than twice the number of dimensions.")
+        ensemble.acceptance[:] = False
+        inds = np.arange(nwalkers) % self.nsplits
+        if self.randomize_split:
+            ensemble.random.shuffle(inds)
+        for i in range(self.nsplits):
+            S1 = inds == i
+            coords = ensemble.coords
+            s = coords[S1]
+            c = coords[~S1]
+            q, factors = self.get_proposal(ensemble, s, c)
+            new = ensemble.propose(q)                                   # ONE batched evaluation
+            old_lp = ensemble.log_probability[S1]
+            u = np.log(ensemble.random.rand(len(new)))
+            for w, f, lp0, uu in zip(new, factors, old_lp, u):
+                lnpdiff = f + w.log_probability - lp0
+                w.accepted = bool(np.isfinite(w.log_probability) and lnpdiff > uu)
+            ensemble.update(new, S1)
+        return ensemble
+
+
+class StretchMove(RedBlueMove):
+    """Goodman & Weare (2010) stretch move with scale ``a``."""
+
+    def __init__(self, a=2.0, **kwargs):
+        self.a = a
+        super(StretchMove, self).__init__(**kwargs)
+
+    def get_proposal(self, ensemble, s, c):
+        Ns, Nc, ndim = len(s), len(c), s.shape[1]
+        zz = ((self.a - 1.0) * ensemble.random.rand(Ns) + 1) ** 2.0 / self.a
+        rint = ensemble.random.randint(Nc, size=Ns)
+        return c[rint] - (c[rint] - s) * zz[:, None], (ndim - 1.0) * np.log(zz)
+
+
+class DEMove(RedBlueMove):
+    """Differential evolution (ter Braak 2006): s + gamma (c_a - c_b), gamma = gamma0 (1 + sigma N(0,1)),
+    gamma0 = 2.38 / sqrt(2 ndim) by default.  gprot/fit.py:84 uses ``DEMove(1.0)`` (sigma = 1)."""
+
+    def __init__(self, sigma=1.0e-5, gamma0=None, **kwargs):
+        self.sigma = sigma
+        self.gamma0 = gamma0
+        super(DEMove, self).__init__(**kwargs)
+
+    def get_proposal(self, ensemble, s, c):
+        Ns, Nc, ndim = len(s), len(c), s.shape[1]
+        g0 = 2.38 / np.sqrt(2 * ndim) if self.gamma0 is None else self.gamma0
+        q = np.empty_like(s)
+        f = self.sigma * ensemble.random.randn(Ns)
+        for i in range(Ns):
+            a, b = ensemble.random.choice(Nc, 2, replace=False)
+            q[i] = s[i] + (c[b] - c[a]) * g0 * (1 + f[i])
+        return q, np.zeros(Ns)
+
+
+class DESnookerMove(RedBlueMove):
+    """Snooker update (ter Braak & Vrugt 2008): move along the line through a third walker z by the projection of
+    the difference of two others.  The Hastings factor is (|q - z| / |s - z|)^(d-1), the Jacobian of a move along a line
+    whose direction depends on s.  (With half that exponent the kernel under-disperses: variance ratio 0.60 on a 5-d
+    Gaussian, tests/test_sampler.py -- the invariance test is the authority here, emcee3 itself cannot be run offline.)"""
+
+    def __init__(self, gammas=1.7, **kwargs):
+        self.gammas = gammas
+        super(DESnookerMove, self).__init__(**kwargs)
+
+    def get_proposal(self, ensemble, s, c):
+        Ns, Nc, ndim = len(s), len(c), s.shape[1]
+        q = np.empty_like(s)
+        metropolis = np.empty(Ns)
+        for i in range(Ns):
+            w = c[ensemble.random.choice(Nc, 3, replace=False)]
+            ensemble.random.shuffle(w)
+            z, z1, z2 = w
+            delta = s[i] - z
+            norm = np.linalg.norm(delta)
+            u = delta / norm
+            q[i] = s[i] + u * self.gammas * (np.dot(u, z1) - np.dot(u, z2))
+            metropolis[i] = np.log(np.linalg.norm(q[i] - z)) - np.log(norm)
+        return q, (ndim - 1.0) * metropolis
+
+
+class KDEMove(RedBlueMove):
+    """Independence proposal drawn from a Gaussian KDE of the complementary ensemble; the Hastings factor is the
+    ratio of the KDE densities."""
+
+    def __init__(self, bw_method=None, **kwargs):
+        self.bw_method = bw_method
+        super(KDEMove, self).__init__(**kwargs)
+
+    def get_proposal(self, ensemble, s, c):
+        from scipy.stats import gaussian_kde
+
+        kde = gaussian_kde(c.T, bw_method=self.bw_method)
+        seed = ensemble.random.randint(0, 2 ** 31 - 1)
+        q = kde.resample(len(s), seed=seed)
+        factor = kde.logpdf(s.T) - kde.logpdf(q)
+        return q.T, factor
+
+
+# ------------------------------------------------------------------------------------------ sampler
+class Sampler(object):
+    """emcee3.Sampler: a (weighted mixture of) move(s) applied to an Ensemble, results stored in a backend."""
+
+    def __init__(self, moves=None, backend=None):
+        if moves is None:
+            self._moves, self._weights = [StretchMove()], [1.0]
+        elif isinstance(moves, (list, tuple)) and len(moves) and isinstance(moves[0], (list, tuple)):
+            self._moves = [m for m, _ in moves]
+            self._weights = [float(w) for _, w in moves]
+        elif isinstance(moves, (list, tuple)):
+            self._moves, self._weights = list(moves), [1.0] * len(moves)
+        else:
+            self._moves, self._weights = [moves], [1.0]
+        self._weights = np.asarray(self._weights) / np.sum(self._weights)
+        self.backend = Backend() if backend is None else backend
+
+    def reset(self):
+        self.backend.reset()
+
+    def sample(self, ensemble, niter=None, store=True, thin=1):
+        if store and niter is not None:
+            self.backend.extend(niter // thin, ensemble.nwalkers, ensemble.ndim)
+        i = 0
+        while niter is None or i < niter:
+            move = self._moves[ensemble.random.choice(len(self._moves), p=self._weights)]
+            ensemble = move.update(ensemble)
+            if store and (i + 1) % thin == 0:
+                self.backend.update(ensemble)
+            i += 1
+            yield ensemble
+
+    def run(self, ensemble, niter, progress=False, **kwargs):
+        it = self.sample(ensemble, niter, **kwargs)
+        if progress:
+            try:
+                from tqdm import tqdm
+
+                it = tqdm(it, total=niter)
+            except Exception:
+                pass
+        for ensemble in it:
+            pass
+        if hasattr(self.backend, "save"):
+            self.backend.save()
+        return ensemble
+
+    # ---- chain access (delegated to the backend, as emcee3 does)
+    def get_coords(self, **kwargs):
+        return self.backend.get_coords(**kwargs)
+
+    def get_log_probability(self, **kwargs):
+        return self.backend.get_log_probability(**kwargs)
+
+    def get_integrated_autocorr_time(self, **kwargs):
+        return self.backend.get_integrated_autocorr_time(**kwargs)
+
+    @property
+    def acceptance_fraction(self):
+        return self.backend.acceptance_fraction

@@ -64,3 +64,27 @@ def synthetic_lightcurve(seed, n, baseline=1400.0, cadence=KEPLER_CADENCE, theta
         raise ValueError("kind must be 'gp' or 'harmonic'")
     y = y + 1e-5 * rng.standard_normal(n)
     return t, y, yerr, theta_true
+
+
+def write_aigrain_dataset(directory, nstars, baseline=1400.0, cadence=KEPLER_CADENCE, seed=0):
+    """Write a synthetic data set in the on-disk layout of the Aigrain et al. (2015) simulations that
+    gprot/aigrain.py reads: ``final/lightcurve_%04d.txt`` (time, 1 + relative flux) and ``par/final_table.txt``
+    (whitespace table with P_MIN / P_MAX columns).  O(N) harmonic signals: this is input plumbing, not the GP."""
+    import os
+
+    os.makedirs(os.path.join(directory, 'final'), exist_ok=True)
+    os.makedirs(os.path.join(directory, 'par'), exist_ok=True)
+    grid = np.arange(0.0, baseline, cadence)
+    rows = []
+    for s in range(nstars):
+        rng = np.random.default_rng(seed + s)
+        th = truth_theta(rng)
+        _, y, _, _ = synthetic_lightcurve(seed + s, grid.size, baseline=baseline, cadence=cadence, theta_true=th, kind='harmonic')
+        np.savetxt(os.path.join(directory, 'final', 'lightcurve_%04d.txt' % s), np.column_stack([grid, 1.0 + y]), fmt='%.10f')
+        P = float(np.exp(th[4]))
+        rows.append((s, P, P))
+    with open(os.path.join(directory, 'par', 'final_table.txt'), 'w') as f:
+        f.write('N P_MIN P_MAX\n')
+        for r in rows:
+            f.write('%d %.6f %.6f\n' % r)
+    return directory

@@ -1,0 +1,94 @@
+"""BASELINE.json configs[4]: end-to-end chain (5000 steps x 64 walkers, KDE/DE/snooker mix) on a synthetic KOI-like light
+curve through GPRotModel -> fit.Emcee3Model -> sampler.Ensemble / Sampler on the GPU, wall clock; beside it the same
+sampler driving the CPU oracle (dense restatement of the george path) for a bounded number of steps, extrapolated.
+
+usage: python tools/bench_chain.py [--steps 5000] [--walkers 64] [--n 2048] [--chunksize 300 | --nochunks] [--cpu-steps 3]
+Prints one JSON line."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from gprotation_b200 import sampler as em  # noqa: E402
+from gprotation_b200.fit import Emcee3Model, EnsemblePool  # noqa: E402
+from gprotation_b200.lc import LightCurve  # noqa: E402
+from gprotation_b200.model import GPRotModel  # noqa: E402
+from gprotation_b200.synth import synthetic_lightcurve  # noqa: E402
+
+
+class OracleModel(object):
+    """The reference's per-walker CPU path: lnprior, then lnlike = sum over chunks (gprot/model.py:358-369)."""
+
+    def __init__(self, t, y, yerr, chunks):
+        from oracle import gp_oracle as o
+
+        self.o, self.t, self.y, self.yerr, self.chunks = o, t, y, yerr, chunks
+
+    def lnprior(self, th):
+        return self.o.lnprior(th)
+
+    def lnlike(self, th):
+        return self.o.lnlike(th, self.t, self.y, self.yerr, self.chunks)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5000)
+    ap.add_argument("--walkers", type=int, default=64)
+    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--chunksize", type=int, default=300)
+    ap.add_argument("--nochunks", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=1)
+    a = ap.parse_args()
+    cs = None if a.nochunks else a.chunksize
+    t, y, yerr, truth = synthetic_lightcurve(a.seed, a.n, kind="harmonic")
+    lc = LightCurve(t, y, yerr, name="koi_like", chunksize=cs)
+    mod = GPRotModel(lc)
+    moves = [(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)]
+    start = mod.sample_from_prior(a.walkers, seed=a.seed)
+
+    ens = em.Ensemble(Emcee3Model(mod), start, pool=EnsemblePool(), random=np.random.RandomState(a.seed))
+    sam = em.Sampler(moves)
+    sam.run(ens, 5)                                              # warm-up: allocations, scipy.stats import
+    sam.reset()
+    l0 = mod.engine.launch_count()
+    t0 = time.perf_counter()
+    sam.run(ens, a.steps)
+    mod.engine.sync()
+    gpu_s = time.perf_counter() - t0
+    launches = mod.engine.launch_count() - l0
+    nchunk = 1 if lc.x_list is None else len(lc.x_list)
+
+    # CPU: identical sampler, one walker at a time through the oracle (the reference's layout with one core)
+    from oracle import gp_oracle as o
+
+    chunks = o.split_chunks(a.n, cs)
+    cpu_model = OracleModel(t, y, yerr, chunks)
+    ens_c = em.Ensemble(Emcee3Model(cpu_model), start, pool=None, random=np.random.RandomState(a.seed))
+    sam_c = em.Sampler(moves)
+    t0 = time.perf_counter()
+    sam_c.run(ens_c, a.cpu_steps)
+    cpu_s_per_step = (time.perf_counter() - t0) / a.cpu_steps
+    cores = len(os.sched_getaffinity(0))
+    line = {
+        "metric": "end-to-end emcee3-style chain wall clock", "unit": "s", "higher_is_better": False,
+        "config": {"workload": "configs[4]: %d steps x %d walkers, N=%d, %s" % (a.steps, a.walkers, a.n,
+                   "one N x N problem (--nochunks)" if cs is None else "%d chunks of <= %d points" % (nchunk, cs))},
+        "value": gpu_s, "ms_per_step": 1e3 * gpu_s / a.steps, "gpu_launches": int(launches),
+        "likelihood_evals": a.steps * a.walkers, "acceptance": float(sam.acceptance_fraction.mean()),
+        "cpu_baseline": {"kind": "port", "cores": 1, "value": cpu_s_per_step * a.steps, "unit": "s",
+                         "sample": "%d steps timed with the same sampler calling the oracle one walker at a time (%.2f s per step), "
+                                   "extrapolated to %d steps; an ideal %d-core pool (the reference's --ncores) would divide this by "
+                                   "at most min(cores, walkers/2) = %d" % (a.cpu_steps, cpu_s_per_step, a.steps, cores,
+                                                                           min(cores, a.walkers // 2))},
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
