@@ -32,6 +32,13 @@ SIGNATURES = {
     "gprot_sync": (c_int, [c_void_p]),
     "gprot_set_cluster": (c_int, [c_void_p, c_int]),
     "gprot_last_cluster": (c_int, [c_void_p]),
+    "gprot_group_create": (c_int, [c_int, c_void_p, POINTER(c_void_p)]),
+    "gprot_group_destroy": (c_int, [c_void_p]),
+    "gprot_group_size": (c_int, [c_void_p]),
+    "gprot_group_last_error": (c_char_p, [c_void_p]),
+    "gprot_group_register_lc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
+    "gprot_group_unregister_all": (c_int, [c_void_p]),
+    "gprot_group_lnlike_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_uint]),
     "gprot_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "gprot_launch_count": (c_int64, [c_void_p]),
     "gprot_measure_dmma_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),

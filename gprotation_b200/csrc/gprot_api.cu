@@ -11,9 +11,16 @@
 #include <limits>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace gprot;
+
+struct gprot_ctx;
+struct gprot_group {
+    std::vector<gprot_ctx*> ctxs;
+    std::string err;
+};
 
 struct gprot_ctx {
     int device = 0;
@@ -528,6 +535,87 @@ int gprot_measure_dmma_peak(gprot_ctx* ctx, double* tflops, double* sm_clock_mhz
     if (sm_clock_mhz) *sm_clock_mhz = (double)c / (best * 1e-3) / 1e6;
     cudaFree(out); cudaFree(cyc); cudaEventDestroy(e0); cudaEventDestroy(e1);
     ctx->launches += 4;
+    return 0;
+}
+
+// ---------------------------------------------------------------- several GPUs from one process
+// (star, walker) rows are independent: contiguous blocks of rows go to the devices of the group, one host thread per
+// device drives its context, the host buffer is the gather.  No device-to-device traffic.
+static int gfail(gprot_group* g, const std::string& msg) {
+    if (g) g->err = msg;
+    g_err = msg;
+    return 1;
+}
+
+int gprot_group_create(int ndev, const int* devices, gprot_group** out) {
+    if (!out) return fail(nullptr, "null out pointer");
+    *out = nullptr;
+    if (ndev <= 0 || !devices) return fail(nullptr, "bad arguments");
+    gprot_group* g = new (std::nothrow) gprot_group;
+    if (!g) return fail(nullptr, "out of host memory");
+    for (int i = 0; i < ndev; i++) {
+        gprot_ctx* c = nullptr;
+        if (gprot_create(devices[i], &c)) {
+            const std::string why = g_err;
+            for (gprot_ctx* x : g->ctxs) gprot_destroy(x);
+            delete g;
+            return fail(nullptr, why);
+        }
+        g->ctxs.push_back(c);
+    }
+    *out = g;
+    return 0;
+}
+
+int gprot_group_destroy(gprot_group* g) {
+    if (!g) return 0;
+    for (gprot_ctx* c : g->ctxs) gprot_destroy(c);
+    delete g;
+    return 0;
+}
+
+int gprot_group_size(const gprot_group* g) { return g ? (int)g->ctxs.size() : 0; }
+
+const char* gprot_group_last_error(const gprot_group* g) { return g ? g->err.c_str() : g_err.c_str(); }
+
+int gprot_group_register_lc(gprot_group* g, int m, const int* n, const double* t, const double* y, const double* yerr, int* lc_id) {
+    if (!g) return fail(nullptr, "null group");
+    int id0 = -1;
+    for (size_t i = 0; i < g->ctxs.size(); i++) {          // light curves are replicated: 24 bytes per point
+        int id = -1;
+        if (gprot_register_lc(g->ctxs[i], m, n, t, y, yerr, &id)) return gfail(g, g->ctxs[i]->err);
+        if (i == 0) id0 = id;
+        else if (id != id0) return gfail(g, "light-curve ids diverged between the devices of the group");
+    }
+    if (lc_id) *lc_id = id0;
+    return 0;
+}
+
+int gprot_group_unregister_all(gprot_group* g) {
+    if (!g) return fail(nullptr, "null group");
+    for (gprot_ctx* c : g->ctxs) gprot_unregister_all(c);
+    return 0;
+}
+
+int gprot_group_lnlike_batch(gprot_group* g, int64_t B, const double* theta, const int32_t* lc_id, double* out, unsigned flags) {
+    if (!g) return fail(nullptr, "null group");
+    if (flags & (GPROT_THETA_ON_DEVICE | GPROT_OUT_ON_DEVICE)) return gfail(g, "gprot_group_lnlike_batch takes host buffers");
+    if (B < 0 || (B > 0 && (!theta || !out))) return gfail(g, "bad arguments");
+    const int64_t G = (int64_t)g->ctxs.size();
+    const int64_t base = B / G, rem = B % G;
+    std::vector<int> rc((size_t)G, 0);
+    std::vector<std::thread> th;
+    for (int64_t r = 0; r < G; r++) {
+        const int64_t lo = r * base + std::min<int64_t>(r, rem), cnt = base + (r < rem ? 1 : 0);
+        if (cnt == 0) continue;
+        gprot_ctx* c = g->ctxs[(size_t)r];
+        th.emplace_back([=, &rc]() {
+            rc[(size_t)r] = lnlike_core(c, cnt, theta + 5 * lo, lc_id ? lc_id + lo : nullptr, nullptr, out + lo, flags, nullptr);
+        });
+    }
+    for (std::thread& t : th) t.join();
+    for (int64_t r = 0; r < G; r++)
+        if (rc[(size_t)r]) return gfail(g, "device " + std::to_string(g->ctxs[(size_t)r]->device) + ": " + g->ctxs[(size_t)r]->err);
     return 0;
 }
 

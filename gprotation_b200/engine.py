@@ -159,3 +159,63 @@ class GPEngine(object):
         out = np.empty(count, dtype=np.float64)
         self._check(self._lib.gprot_debug_read_scratch(self._ctx, slot, offset, count, out.ctypes.data))
         return out
+
+
+class GPGroup(object):
+    """Several GPUs driven from one process (gprot_group_* in include/gprot_b200.h): rows of a batch are block-sharded
+    over the devices, light curves are replicated, the host buffer is the gather.  Same register / lnlike surface as
+    GPEngine, so GPRotModel(engine=GPGroup([0, 1, ...])) uses the whole box."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        self._grp = c_void_p()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._lib.gprot_group_create(int(dev.size), dev.ctypes.data, byref(self._grp))
+        if rc != 0:
+            raise GProtError(self._lib.gprot_group_last_error(None).decode())
+        self.devices = [int(d) for d in dev]
+
+    def close(self):
+        if getattr(self, "_grp", None) is not None and self._grp.value:
+            self._lib.gprot_group_destroy(self._grp)
+            self._grp = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GProtError(self._lib.gprot_group_last_error(self._grp).decode())
+
+    def __len__(self):
+        return int(self._lib.gprot_group_size(self._grp))
+
+    def register_lc(self, t, y, yerr, chunks=None):
+        t, y, yerr = _f64(t), _f64(y), _f64(yerr)
+        if chunks is None:
+            return self.register_lc_arrays([t], [y], [yerr])
+        chunks = [np.asarray(c) for c in chunks]
+        return self.register_lc_arrays([t[c] for c in chunks], [y[c] for c in chunks], [yerr[c] for c in chunks])
+
+    def register_lc_arrays(self, x_list, y_list, yerr_list):
+        n = np.array([len(x) for x in x_list], dtype=np.int32)
+        tt, yy, ee = _f64(np.concatenate(x_list)), _f64(np.concatenate(y_list)), _f64(np.concatenate(yerr_list))
+        lc_id = c_int(-1)
+        self._check(self._lib.gprot_group_register_lc(self._grp, int(n.size), n.ctypes.data, tt.ctypes.data, yy.ctypes.data,
+                                                      ee.ctypes.data, byref(lc_id)))
+        return lc_id.value
+
+    def unregister_all(self):
+        self._check(self._lib.gprot_group_unregister_all(self._grp))
+
+    def lnlike_batch(self, theta, lc_id=None, exact=False):
+        theta = _f64(theta).reshape(-1, 5)
+        B = theta.shape[0]
+        out = np.empty(B, dtype=np.float64)
+        ids = GPEngine._ids(lc_id, B)
+        self._check(self._lib.gprot_group_lnlike_batch(self._grp, B, theta.ctypes.data, ids.ctypes.data if ids is not None else None,
+                                                       out.ctypes.data, _lib.EXACT_KERNEL if exact else 0))
+        return out

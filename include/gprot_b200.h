@@ -85,6 +85,23 @@ int gprot_sync(gprot_ctx *ctx);
 int gprot_set_cluster(gprot_ctx *ctx, int ctas_per_problem);
 int gprot_last_cluster(const gprot_ctx *ctx);
 
+/* Several GPUs from ONE process (replaces the reference's one-process-per-core MultiPool /
+ * MPIPool fan-out of scripts/gprot-fit:127-131,195 when a single driver process owns the box).  A group holds one
+ * context per listed device; light curves are replicated to every device; gprot_group_lnlike_batch gives device r
+ * the r-th contiguous block of rows (star-major row lists keep a star's walkers together), drives the devices
+ * concurrently and gathers into the caller's host buffer -- no device-to-device traffic.  One process per GPU with
+ * a distributed launcher (gprotation_b200/dist.py, NCCL all-gather of the log-probabilities) is the multi-process form. */
+typedef struct gprot_group gprot_group;
+int gprot_group_create(int ndev, const int *devices, gprot_group **grp);
+int gprot_group_destroy(gprot_group *grp);
+int gprot_group_size(const gprot_group *grp);
+const char *gprot_group_last_error(const gprot_group *grp);
+int gprot_group_register_lc(gprot_group *grp, int m, const int *n, const double *t, const double *y,
+                            const double *yerr, int *lc_id);
+int gprot_group_unregister_all(gprot_group *grp);
+int gprot_group_lnlike_batch(gprot_group *grp, int64_t B, const double *theta, const int32_t *lc_id,
+                             double *out, unsigned flags);
+
 /* Measurement hooks (bench.py): device time of the last likelihood launch, CUDA events on the
  * launching stream; number of kernels launched by this context so far; FP64 tensor (DMMA) peak
  * of this device measured by a register-resident mma.sync.m8n8k4.f64 loop. */

@@ -298,3 +298,38 @@ def test_cluster_auto_choice(engine):
     big = engine.lnlike_batch(th, lc_id=lc)
     assert engine.last_cluster() == 1
     assert np.array_equal(small, big[:16])
+
+
+def test_group_shards_rows_over_contexts(engine):
+    """gprot_group_*: rows block-sharded over the contexts of a group, host buffer is the gather.  On a one-GPU box the
+    group holds two contexts on device 0 -- the sharding, replication and gather logic is the same code."""
+    import torch
+
+    from gprotation_b200 import GPGroup
+
+    ndev = torch.cuda.device_count()
+    devices = [0, 1 % ndev, 0][: 3 if ndev == 1 else 2]
+    grp = GPGroup(devices)
+    try:
+        assert len(grp) == len(devices)
+        engine.unregister_all()
+        ids_g, ids_e, lcs = [], [], []
+        for s in range(3):
+            t, y, yerr, _ = synthetic_lightcurve(40 + s, 200 + 60 * s, baseline=100.0, kind="harmonic")
+            ch = o.split_chunks(len(t), 150 if s == 1 else None)
+            ids_g.append(grp.register_lc(t, y, yerr, chunks=ch))
+            ids_e.append(engine.register_lc(t, y, yerr, chunks=ch))
+            lcs.append((t, y, yerr, ch))
+        assert ids_g == ids_e
+        th = o.sample_from_prior(17, seed=77)                   # 17 rows over 2 or 3 contexts: uneven blocks
+        ids = np.array([ids_g[i % 3] for i in range(17)], dtype=np.int32)
+        got = grp.lnlike_batch(th, lc_id=ids)
+        one = engine.lnlike_batch(th, lc_id=ids)
+        assert np.array_equal(got, one)                          # same kernel, same order of operations
+        ref = np.array([o.lnlike(x, *lcs[i % 3][:3], lcs[i % 3][3]) for i, x in enumerate(th)])
+        assert np.all(np.abs(got - ref) <= 1e-9 * np.abs(ref))
+        assert np.array_equal(grp.lnlike_batch(th[:1], lc_id=ids[:1]), one[:1])      # fewer rows than devices
+        with pytest.raises(Exception):
+            grp.lnlike_batch(th, lc_id=np.full(17, 99, dtype=np.int32))
+    finally:
+        grp.close()
