@@ -290,7 +290,7 @@ def run_ours(args):
                        "l2": "no flush: each step streams %.0f GB of factor scratch (2.3 GB working set) through a 126 MB L2"
                              % (B * factor_stream_bytes_per_eval(n) / 1e9)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": args.traffic, "kernel": "gp_lnlike_kernel<false>", "kernel_ms": kernel_ms,
+                         "traffic": args.traffic, "kernel": "gp_lnlike_kernel<false,1>", "kernel_ms": kernel_ms,
                          "flops_per_launch": B * F,
                          "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) register-resident loop measured live on this GPU at "
                                         "%.0f MHz; MEASURED_PEAKS.json has no fp64 entry; cuBLAS DGEMM 8192^3 on this pool: 35.5 TFLOP/s"
@@ -324,7 +324,9 @@ def cpu_baseline_worker():
     # ~0.4 s per N=2048 evaluation per core: 2 per core x (1 warm-up + 2 timed passes) stays within ~10-30 s
     rate, cores, nev, times = cpu_pool_rate(N_POINTS, 2, steps=2, warmup=1, cores=cores)
     single_ms = 1e3 * sum(times) / len(times) / 2
-    print(json.dumps({"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+    # BASELINE configs[0] beside it: N=1000, 32 walkers on the same pool
+    c1_rate, _, c1_nev, _ = cpu_pool_rate(1000, max(1, 32 // cores), steps=2, warmup=1, cores=min(cores, 32))
+    print(json.dumps({"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "c1_n1000_evals_per_s": c1_rate,
                       "sample": "%d evals per pass (2 per core), 2 timed passes, N=2048, same synthetic star generator; "
                                 "one single-threaded NumPy/LAPACK process per core (the reference's --ncores MultiPool layout); "
                                 "%.0f ms per evaluation per core" % (nev, single_ms)}))

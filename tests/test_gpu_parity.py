@@ -333,3 +333,53 @@ def test_group_shards_rows_over_contexts(engine):
             grp.lnlike_batch(th, lc_id=np.full(17, 99, dtype=np.int32))
     finally:
         grp.close()
+
+
+def test_long_baseline_stress_shape(engine):
+    """BASELINE config 4 shape (N=8192, few proposals per GPU -> every problem spread over a thread-block cluster):
+    one row against the oracle, scaling property and cluster-size independence on the rest."""
+    n, c = 8192, 3.0
+    t, y, yerr, _ = synthetic_lightcurve(7, n, kind="harmonic")
+    th = o.sample_from_prior(6, seed=55)
+    th2 = th.copy()
+    th2[:, 0] += 2 * math.log(c)
+    th2[:, 3] += 2 * math.log(c)
+    engine.unregister_all()
+    a = engine.register_lc(t, y, yerr)
+    s = engine.register_lc(t, c * y, c * yerr)
+    try:
+        engine.set_cluster(0)
+        base = engine.lnlike_batch(th, lc_id=a)
+        assert engine.last_cluster() > 1                                  # 6 problems on 148 SMs
+        scal = engine.lnlike_batch(th2, lc_id=s)
+        engine.set_cluster(1)
+        one = engine.lnlike_batch(th[:2], lc_id=a)
+        assert np.array_equal(one, base[:2])
+    finally:
+        engine.set_cluster(0)
+    ref = o.lnlike_function(th[0], t, y, yerr)
+    assert abs(base[0] - ref) <= 1e-9 * abs(ref)
+    m = np.isfinite(base)
+    assert m.sum() >= 4
+    assert np.all(np.abs(scal[m] - (base[m] - n * math.log(c))) <= 1e-8 * np.abs(base[m]))
+
+
+def test_multi_star_sweep_shape(engine):
+    """BASELINE config 3 shape in miniature: many stars x 64 walkers in ONE launch, rows star-major; every star's rows
+    equal a launch of that star alone, and a sample matches the oracle."""
+    nstar, W, n = 12, 64, 700
+    engine.unregister_all()
+    lcs, ids = [], []
+    for s in range(nstar):
+        t, y, yerr, _ = synthetic_lightcurve(300 + s, n, baseline=500.0, kind="harmonic")
+        ids.append(engine.register_lc(t, y, yerr))
+        lcs.append((t, y, yerr))
+    th = o.sample_from_prior(nstar * W, seed=91)
+    rows = np.repeat(np.array(ids, dtype=np.int32), W)
+    allrows = engine.lnlike_batch(th, lc_id=rows)
+    for s in (0, 5, nstar - 1):
+        alone = engine.lnlike_batch(th[s * W:(s + 1) * W], lc_id=ids[s])
+        assert np.array_equal(alone, allrows[s * W:(s + 1) * W])
+        k = s * W + 17
+        ref = o.lnlike_function(th[k], *lcs[s])
+        assert abs(allrows[k] - ref) <= 1e-9 * max(1.0, cond_of(th[k], lcs[s][0], lcs[s][2]) / 1e7) * abs(ref)
