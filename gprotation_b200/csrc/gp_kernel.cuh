@@ -928,7 +928,9 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             __syncthreads();
             // ================= diagonal block (J, J)
             {
-                const bool active = wr >= wc;
+                // the last block may be mostly identity padding: warp rows beyond the real points do no work at all
+                const int ractJ = (J == T - 1) ? ((n - J * BS + 31) >> 5) : 4;
+                const bool active = wr >= wc && wr < ractJ;
                 if (tid == 0) prologue<true>(sm, it, jrow, jrow, niter);
                 if (active) synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, J * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
                 TICK(1);
@@ -943,8 +945,8 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                         for (int ni = 0; ni < 4; ni++) {
                             const int r = 32 * wr + 8 * mi + g, c = 32 * wc + 8 * ni + 2 * q;
                             double2 v;
-                            v.x = (active && r >= c) ? -acc[mi][ni][0] : 0.0;
-                            v.y = (active && r >= c + 1) ? -acc[mi][ni][1] : 0.0;
+                            v.x = (active && r >= c) ? -acc[mi][ni][0] : ((wr >= ractJ && r == c) ? 1.0 : 0.0);
+                            v.y = (active && r >= c + 1) ? -acc[mi][ni][1] : ((wr >= ractJ && r == c + 1) ? 1.0 : 0.0);
                             *reinterpret_cast<double2*>(M + r * LDM + c) = v;
                         }
                     if (tid < BS) sm.yj[tid] = yw[J * BS + tid];
@@ -978,15 +980,22 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             // ================= blocks below the diagonal (their first slabs are already in flight)
             for (int I = I0; I < T; I += CL) {
                 const double* irow = lbase + (size_t)(I * (I - 1) / 2) * BLKD;
-                if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
-                else                                synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
+                // Warp rows of the last block row that hold only identity padding skip everything but the barriers:
+                // their rows of L are never read by a warp that works (operands are consumed by the same warp row).
+                const int ract = (I == T - 1) ? ((n - I * BS + 31) >> 5) : 4;
+                const bool rowact = wr < ract;
+                if (rowact) {
+                    if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
+                    else                                synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
+                }
                 TICK(6);
-                accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, true);
+                accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, rowact);
                 __syncthreads();                                   // stages drained: regionA becomes the S_IJ staging block
                 TICK(7);
-                store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc
+                if (rowact) store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc
                 __syncthreads();
                 TICK(8);
+                if (rowact) {
                 // ---- L_IJ = S W^T : k runs over m <= c
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++)
@@ -1055,13 +1064,14 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 // stored as each warp finishes: warps with a short triangular product overlap their stores with the
                 // others' DMMAs
                 store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
+                }
                 if (I + CL < T) stage_points(sm.rowv, vt, prm.npad_max, I + CL, tid);   // row side of the next block
                 fence_async();
                 __syncthreads();                                   // staging reads done (regionA free again), partials visible
                 TICK(9);
                 if (tid == 0 && I + CL < T)                        // next block's first slabs fly during its synthesis
                     prologue<false>(sm, it, lbase + (size_t)((I + CL) * (I + CL - 1) / 2) * BLKD, jrow, niter);
-                if (tid < BS) {
+                if (tid < 32 * ract) {
                     const int r = tid;
                     yw[I * BS + r] -= (sm.red[r] + sm.red[BS + r]) + (sm.red[2 * BS + r] + sm.red[3 * BS + r]);
                 }
