@@ -383,3 +383,25 @@ def test_multi_star_sweep_shape(engine):
         k = s * W + 17
         ref = o.lnlike_function(th[k], *lcs[s])
         assert abs(allrows[k] - ref) <= 1e-9 * max(1.0, cond_of(th[k], lcs[s][0], lcs[s][2]) / 1e7) * abs(ref)
+
+
+def test_repeated_launches_are_bitwise_stable(engine):
+    """Race detector of last resort (compute-sanitizer is not available on the GPU pool): the warp-specialised diagonal
+    sweep, the named-barrier hand-over, the cluster barriers and the work queue must give the same bits on every run,
+    whatever the scheduling.  Mixed problem sizes in one launch make CTAs take problems in a different order each time."""
+    engine.unregister_all()
+    ids = []
+    for s, (n, cs) in enumerate([(1100, None), (700, 250), (129, None), (300, 100), (1536, None)]):
+        t, y, yerr, _ = synthetic_lightcurve(900 + s, n, baseline=600.0, kind="harmonic")
+        ids.append(engine.register_lc(t, y, yerr, chunks=o.split_chunks(n, cs)))
+    th = o.sample_from_prior(400, seed=12)
+    rows = np.array([ids[i % len(ids)] for i in range(400)], dtype=np.int32)
+    try:
+        for cl in (0, 1, 2, 4):
+            engine.set_cluster(cl)
+            n_rows = 400 if cl in (0, 1) else 48
+            first = engine.lnlike_batch(th[:n_rows], lc_id=rows[:n_rows])
+            for _ in range(12):
+                assert np.array_equal(engine.lnlike_batch(th[:n_rows], lc_id=rows[:n_rows]), first), cl
+    finally:
+        engine.set_cluster(0)
