@@ -28,7 +28,7 @@ import numpy as np
 from .fit import Emcee3Model, EnsemblePool, State
 
 __all__ = ["AutocorrError", "integrated_time", "Backend", "NPZBackend", "HDFBackend", "Ensemble", "Sampler",
-           "StretchMove", "DEMove", "DESnookerMove", "KDEMove", "DefaultPool", "Model", "State"]
+           "Proposal", "StretchMove", "DEMove", "DESnookerMove", "KDEMove", "DefaultPool", "Model", "State"]
 
 Model = Emcee3Model
 
@@ -220,63 +220,110 @@ def HDFBackend(filename, **kwargs):
 
 
 # ------------------------------------------------------------------------------------------ ensemble
+class Proposal(object):
+    """The evaluated states of one proposal set, as arrays (what ``Ensemble.propose`` returns).  Iterating yields
+    ``State`` objects for code written against the per-walker emcee3 interface."""
+
+    def __init__(self, coords, log_prior, log_likelihood):
+        self.coords = np.asarray(coords, dtype=np.float64)
+        lp = np.asarray(log_prior, dtype=np.float64)
+        ll = np.asarray(log_likelihood, dtype=np.float64)
+        ok = np.isfinite(lp)
+        self.log_prior = np.where(ok, lp, -np.inf)
+        self.log_likelihood = np.where(ok & np.isfinite(ll), ll, -np.inf)
+        self.accepted = np.zeros(len(self.coords), dtype=bool)
+
+    @property
+    def log_probability(self):
+        with np.errstate(invalid="ignore"):
+            p = self.log_prior + self.log_likelihood
+        return np.where(np.isfinite(p), p, -np.inf)
+
+    def __len__(self):
+        return len(self.coords)
+
+    def __iter__(self):
+        for c, a, b, acc in zip(self.coords, self.log_prior, self.log_likelihood, self.accepted):
+            yield State(c, float(a), float(b), bool(acc))
+
+
 class Ensemble(object):
     """The walkers (emcee3.Ensemble): ``model`` maps a State to a State with log_prior / log_likelihood filled in;
-    all states of a proposal set go through ``pool.map`` in ONE call."""
+    all states of a proposal set go through the pool in ONE call.  State is kept as arrays; ``walkers`` builds the
+    emcee3-style list of State objects on demand."""
 
     def __init__(self, model, coords, pool=None, random=None):
         self.model = model
         self.pool = DefaultPool() if pool is None else pool
         self.random = np.random.RandomState() if random is None else random
-        coords = np.atleast_2d(np.asarray(coords, dtype=np.float64))
-        self.walkers = self.propose(coords)
-        self.acceptance = np.ones(len(self.walkers), dtype=bool)
+        first = self.propose(np.atleast_2d(np.asarray(coords, dtype=np.float64)))
+        self._coords = first.coords.copy()
+        self._log_prior = first.log_prior.copy()
+        self._log_likelihood = first.log_likelihood.copy()
+        self.acceptance = np.ones(len(first), dtype=bool)
         if not np.all(np.isfinite(self.log_probability)):
             raise ValueError("invalid or zero-probability coordinates for at least one walker")
 
     def propose(self, coords):
-        states = [State(c) for c in np.atleast_2d(coords)]
-        return list(self.pool.map(self.model, states))
+        coords = np.atleast_2d(np.asarray(coords, dtype=np.float64))
+        model = self.model
+        if isinstance(model, Emcee3Model) and hasattr(model.mod, "lnpost_batch") and isinstance(self.pool, (DefaultPool, EnsemblePool)):
+            lp, ll = model.mod.lnpost_batch(coords, return_parts=True)        # the whole proposal set: one launch
+            return Proposal(coords, lp, ll)
+        states = list(self.pool.map(model, [State(c) for c in coords]))
+        return Proposal(coords, [w.log_prior for w in states], [w.log_likelihood for w in states])
 
-    def update(self, walkers, subset=None):
+    def update(self, proposal, subset=None):
         """Replace the walkers of ``subset`` (boolean mask) by the accepted proposals."""
-        idx = np.arange(len(self.walkers)) if subset is None else np.flatnonzero(subset)
-        if len(idx) != len(walkers):
+        idx = np.arange(self.nwalkers) if subset is None else np.flatnonzero(subset)
+        if len(idx) != len(proposal):
             raise ValueError("subset and proposal sizes differ")
-        for j, w in zip(idx, walkers):
-            self.acceptance[j] = bool(w.accepted)
-            if w.accepted:
-                self.walkers[j] = w
+        acc = np.asarray(proposal.accepted, dtype=bool)
+        self.acceptance[idx] = acc
+        j = idx[acc]
+        self._coords[j] = proposal.coords[acc]
+        self._log_prior[j] = proposal.log_prior[acc]
+        self._log_likelihood[j] = proposal.log_likelihood[acc]
 
     def __len__(self):
-        return len(self.walkers)
+        return self.nwalkers
+
+    @property
+    def walkers(self):
+        return [State(c, float(a), float(b), bool(acc))
+                for c, a, b, acc in zip(self._coords, self._log_prior, self._log_likelihood, self.acceptance)]
 
     @property
     def nwalkers(self):
-        return len(self.walkers)
+        return self._coords.shape[0]
 
     @property
     def ndim(self):
-        return len(self.walkers[0].coords)
+        return self._coords.shape[1]
 
     @property
     def coords(self):
-        return np.stack([w.coords for w in self.walkers])
+        return self._coords
 
     @property
     def log_prior(self):
-        return np.array([w.log_prior for w in self.walkers], dtype=np.float64)
+        return self._log_prior
 
     @property
     def log_likelihood(self):
-        return np.array([w.log_likelihood for w in self.walkers], dtype=np.float64)
+        return self._log_likelihood
 
     @property
     def log_probability(self):
-        return np.array([w.log_probability for w in self.walkers], dtype=np.float64)
+        return self._log_prior + self._log_likelihood
 
 
 # ------------------------------------------------------------------------------------------ moves
+def _distinct(random, n, k, rows):
+    """``rows`` independent draws of k distinct indices out of n, in random order (uniform over ordered k-tuples)."""
+    return np.argsort(random.rand(rows, n), axis=1)[:, :k]
+
+
 class RedBlueMove(object):
     """Split the walkers into ``nsplits`` groups; each group is moved using the others as the complementary
     ensemble, which keeps detailed balance while the whole group is proposed -- and evaluated -- at once."""
@@ -300,15 +347,12 @@ class RedBlueMove(object):
         for i in range(self.nsplits):
             S1 = inds == i
             coords = ensemble.coords
-            s = coords[S1]
-            c = coords[~S1]
-            q, factors = self.get_proposal(ensemble, s, c)
+            q, factors = self.get_proposal(ensemble, coords[S1], coords[~S1])
             new = ensemble.propose(q)                                   # ONE batched evaluation
-            old_lp = ensemble.log_probability[S1]
-            u = np.log(ensemble.random.rand(len(new)))
-            for w, f, lp0, uu in zip(new, factors, old_lp, u):
-                lnpdiff = f + w.log_probability - lp0
-                w.accepted = bool(np.isfinite(w.log_probability) and lnpdiff > uu)
+            new_lp = new.log_probability
+            with np.errstate(invalid="ignore"):
+                lnpdiff = factors + new_lp - ensemble.log_probability[S1]
+            new.accepted = np.isfinite(new_lp) & (lnpdiff > np.log(ensemble.random.rand(len(new))))
             ensemble.update(new, S1)
         return ensemble
 
@@ -339,11 +383,9 @@ class DEMove(RedBlueMove):
     def get_proposal(self, ensemble, s, c):
         Ns, Nc, ndim = len(s), len(c), s.shape[1]
         g0 = 2.38 / np.sqrt(2 * ndim) if self.gamma0 is None else self.gamma0
-        q = np.empty_like(s)
         f = self.sigma * ensemble.random.randn(Ns)
-        for i in range(Ns):
-            a, b = ensemble.random.choice(Nc, 2, replace=False)
-            q[i] = s[i] + (c[b] - c[a]) * g0 * (1 + f[i])
+        ab = _distinct(ensemble.random, Nc, 2, Ns)
+        q = s + (c[ab[:, 1]] - c[ab[:, 0]]) * (g0 * (1 + f))[:, None]
         return q, np.zeros(Ns)
 
 
@@ -359,36 +401,45 @@ class DESnookerMove(RedBlueMove):
 
     def get_proposal(self, ensemble, s, c):
         Ns, Nc, ndim = len(s), len(c), s.shape[1]
-        q = np.empty_like(s)
-        metropolis = np.empty(Ns)
-        for i in range(Ns):
-            w = c[ensemble.random.choice(Nc, 3, replace=False)]
-            ensemble.random.shuffle(w)
-            z, z1, z2 = w
-            delta = s[i] - z
-            norm = np.linalg.norm(delta)
-            u = delta / norm
-            q[i] = s[i] + u * self.gammas * (np.dot(u, z1) - np.dot(u, z2))
-            metropolis[i] = np.log(np.linalg.norm(q[i] - z)) - np.log(norm)
+        w = _distinct(ensemble.random, Nc, 3, Ns)
+        z, z1, z2 = c[w[:, 0]], c[w[:, 1]], c[w[:, 2]]
+        delta = s - z
+        norm = np.sqrt(np.sum(delta * delta, axis=1))
+        u = delta / norm[:, None]
+        q = s + u * (self.gammas * (np.sum(u * z1, axis=1) - np.sum(u * z2, axis=1)))[:, None]
+        metropolis = np.log(np.sqrt(np.sum((q - z) ** 2, axis=1))) - np.log(norm)
         return q, (ndim - 1.0) * metropolis
 
 
 class KDEMove(RedBlueMove):
-    """Independence proposal drawn from a Gaussian KDE of the complementary ensemble; the Hastings factor is the
+    """Independence proposal drawn from a Gaussian KDE of the complementary ensemble (bandwidth: Scott's rule on the
+    sample covariance, as scipy.stats.gaussian_kde, or ``bw_method`` = a scalar factor); the Hastings factor is the
     ratio of the KDE densities."""
 
     def __init__(self, bw_method=None, **kwargs):
         self.bw_method = bw_method
         super(KDEMove, self).__init__(**kwargs)
 
-    def get_proposal(self, ensemble, s, c):
-        from scipy.stats import gaussian_kde
+    @staticmethod
+    def _logpdf(x, data, chol):
+        # log (1/n) sum_j N(x - data_j; C),  C = chol chol^T
+        n, d = data.shape
+        from scipy.linalg import solve_triangular
 
-        kde = gaussian_kde(c.T, bw_method=self.bw_method)
-        seed = ensemble.random.randint(0, 2 ** 31 - 1)
-        q = kde.resample(len(s), seed=seed)
-        factor = kde.logpdf(s.T) - kde.logpdf(q)
-        return q.T, factor
+        diff = x[:, None, :] - data[None, :, :]                                       # [m, n, d]
+        y = solve_triangular(chol, diff.reshape(-1, d).T, lower=True).T.reshape(len(x), n, d)
+        e = -0.5 * np.sum(y * y, axis=2)
+        mx = np.max(e, axis=1, keepdims=True)
+        lse = mx[:, 0] + np.log(np.sum(np.exp(e - mx), axis=1))
+        return lse - np.log(n) - 0.5 * d * np.log(2 * np.pi) - np.sum(np.log(np.diag(chol)))
+
+    def get_proposal(self, ensemble, s, c):
+        n, d = c.shape
+        factor = n ** (-1.0 / (d + 4)) if self.bw_method is None else float(self.bw_method)
+        chol = np.linalg.cholesky(np.atleast_2d(np.cov(c, rowvar=False)) * factor ** 2)
+        pick = ensemble.random.randint(n, size=len(s))
+        q = c[pick] + ensemble.random.randn(len(s), d) @ chol.T
+        return q, self._logpdf(s, c, chol) - self._logpdf(q, c, chol)
 
 
 # ------------------------------------------------------------------------------------------ sampler
