@@ -65,6 +65,7 @@ struct Smem {
     unsigned long long empty[STAGES];
     int prob;
     int fail;
+    int prob2;                    // block row handed out by the per-column counter (cluster kernels)
 };
 
 struct Params {
@@ -86,6 +87,10 @@ struct Params {
     double* vscratch;             // per-slot vectors: t (clamped), sin, cos, diag, ytilde (5 * npad_max)
     int npad_max;
     long long* timing;            // [16] per-phase cycle totals of CTA 0 (only written when built with -DGPROT_TIMING)
+    double* wg;                   // cluster kernels, per slot: 2 x [W | z] exchange buffers, then per-column sums (2 x tcap)
+    size_t wg_stride;             // doubles
+    int* cctr;                    // cluster kernels, per slot: failure flag + per-column row counters (2 + tcap ints)
+    int tcap;                     // capacity in block columns of the per-column arrays
 };
 
 #ifdef GPROT_TIMING
@@ -911,6 +916,10 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             }
             vt[i] = ti; vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
         }
+        if (CL > 1 && crank == 0) {                              // failure flag and per-column row counters of this problem
+            int* const ctr0 = prm.cctr + (size_t)slot * (prm.tcap + 2);
+            for (int i = tid; i < T + 1; i += NT) ctr0[i] = 0;
+        }
         if (CL > 1) cluster_sync(); else __syncthreads();
         TICK(0);
 
@@ -918,15 +927,12 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         double acc[4][4][2];
         bool failed = false;
 
-        for (int J = 0; J < T && !failed; J++) {
+        // ---- diagonal block (J, J): S_JJ, its factor, W = L_JJ^{-1} (sm.W), z_J (sm.zs), partial sums (sm.qpart / lpart).
+        // Expects sm.colv / sm.rowv staged for block J.  nextI >= 0: stage the row side of block row nextI and start its
+        // first TMA slabs on the way out.  Returns false if a pivot failed.
+        auto diag_block = [&](const int J, const int nextI) -> bool {
             const double* jrow = lbase + (size_t)(J * (J - 1) / 2) * BLKD;   // blocks (J, 0..J-1), contiguous
             const int niter = 8 * J;
-            // first block row of this column owned by this CTA (rows are dealt round-robin: I mod CL)
-            const int I0 = CL > 1 ? J + 1 + ((crank - (J + 1)) % CL + CL) % CL : J + 1;
-            stage_points(sm.colv, vt, prm.npad_max, J, tid);       // per-point values of block J: column side ...
-            stage_points(sm.rowv, vt, prm.npad_max, J, tid);        // ... and row side of the diagonal tile
-            __syncthreads();
-            // ================= diagonal block (J, J)
             {
                 // the last block may be mostly identity padding: warp rows beyond the real points do no work at all
                 const int ractJ = (J == T - 1) ? ((n - J * BS + 31) >> 5) : 4;
@@ -963,23 +969,28 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                     }
                 }
                 TICK(4);
-                if (sm.fail) { failed = true; break; }
-                diag_solve(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
-                if (I0 < T) stage_points(sm.rowv, vt, prm.npad_max, I0, tid);   // row side of the first block below
-                fence_async();
-                __syncthreads();
-                TICK(5);
-                if (tid == 0) {
-                    double qs = 0.0, ls = 0.0;
-                    for (int w = 0; w < 16; w++) { qs += sm.qpart[w]; ls += sm.lpart[w]; }    // fixed order
-                    quad += qs;
-                    logdet += ls;
-                }
             }
-            if (tid == 0 && I0 < T) prologue<false>(sm, it, lbase + (size_t)(I0 * (I0 - 1) / 2) * BLKD, jrow, niter);
-            // ================= blocks below the diagonal (their first slabs are already in flight)
-            for (int I = I0; I < T; I += CL) {
-                const double* irow = lbase + (size_t)(I * (I - 1) / 2) * BLKD;
+            if (sm.fail) return false;
+            diag_solve(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
+            if (nextI >= 0) stage_points(sm.rowv, vt, prm.npad_max, nextI, tid);   // row side of the first block below
+            fence_async();
+            __syncthreads();
+            TICK(5);
+            if (tid == 0 && nextI >= 0) prologue<false>(sm, it, lbase + (size_t)(nextI * (nextI - 1) / 2) * BLKD, jrow, niter);
+            return true;
+        };
+
+        // ---- block (I, J) below the diagonal: S_IJ, L_IJ = S_IJ W^T, ytilde_I -= L_IJ z_J, store L_IJ.
+        // staged: sm.rowv holds block row I and its first slabs are in flight (set up by the previous call through nextI).
+        auto offdiag_block = [&](const int I, const int J, const int nextI, const bool staged) {
+            const double* jrow = lbase + (size_t)(J * (J - 1) / 2) * BLKD;
+            const double* irow = lbase + (size_t)(I * (I - 1) / 2) * BLKD;
+            const int niter = 8 * J;
+            if (!staged) {
+                stage_points(sm.rowv, vt, prm.npad_max, I, tid);
+                __syncthreads();
+                if (tid == 0) prologue<false>(sm, it, irow, jrow, niter);
+            }
                 // Warp rows of the last block row that hold only identity padding skip everything but the barriers:
                 // their rows of L are never read by a warp that works (operands are consumed by the same warp row).
                 const int ract = (I == T - 1) ? ((n - I * BS + 31) >> 5) : 4;
@@ -1065,23 +1076,119 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 // others' DMMAs
                 store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
                 }
-                if (I + CL < T) stage_points(sm.rowv, vt, prm.npad_max, I + CL, tid);   // row side of the next block
-                fence_async();
-                __syncthreads();                                   // staging reads done (regionA free again), partials visible
-                TICK(9);
-                if (tid == 0 && I + CL < T)                        // next block's first slabs fly during its synthesis
-                    prologue<false>(sm, it, lbase + (size_t)((I + CL) * (I + CL - 1) / 2) * BLKD, jrow, niter);
-                if (tid < 32 * ract) {
-                    const int r = tid;
-                    yw[I * BS + r] -= (sm.red[r] + sm.red[BS + r]) + (sm.red[2 * BS + r] + sm.red[3 * BS + r]);
-                }
-                TICK(10);
-            }
-            // blocks of column J are first read (by TMA, the async proxy) in column J+1: one fence per column
-            __threadfence();
+            if (nextI >= 0) stage_points(sm.rowv, vt, prm.npad_max, nextI, tid);   // row side of the next block
             fence_async();
-            if (CL > 1) { cluster_sync(); fence_async(); } else __syncthreads();
-            TICK(11);
+            __syncthreads();                                   // staging reads done (regionA free again), partials visible
+            TICK(9);
+            if (tid == 0 && nextI >= 0)                        // next block's first slabs fly during its synthesis
+                prologue<false>(sm, it, lbase + (size_t)(nextI * (nextI - 1) / 2) * BLKD, jrow, niter);
+            if (tid < 32 * ract) {
+                const int r = tid;
+                yw[I * BS + r] -= (sm.red[r] + sm.red[BS + r]) + (sm.red[2 * BS + r] + sm.red[3 * BS + r]);
+            }
+            TICK(10);
+        };
+
+        auto column_sums = [&](double& qs, double& ls) {       // fixed order: deterministic
+            qs = 0.0; ls = 0.0;
+            for (int w = 0; w < 16; w++) { qs += sm.qpart[w]; ls += sm.lpart[w]; }
+        };
+
+        if (CL == 1) {
+            for (int J = 0; J < T; J++) {
+                stage_points(sm.colv, vt, prm.npad_max, J, tid);       // per-point values of block J: column side ...
+                stage_points(sm.rowv, vt, prm.npad_max, J, tid);       // ... and row side of the diagonal tile
+                __syncthreads();
+                if (!diag_block(J, J + 1 < T ? J + 1 : -1)) { failed = true; break; }
+                if (tid == 0) {
+                    double qs, ls;
+                    column_sums(qs, ls);
+                    quad += qs;
+                    logdet += ls;
+                }
+                for (int I = J + 1; I < T; I++) offdiag_block(I, J, I + 1 < T ? I + 1 : -1, true);
+                // blocks of column J are first read (by TMA, the async proxy) in column J+1: one fence per column
+                __threadfence();
+                fence_async();
+                __syncthreads();
+                TICK(11);
+            }
+        } else {
+            // ---- CL CTAs share the problem.  Block rows of a column are handed out by a per-column counter (whoever is
+            // free takes the next one); the CTA that takes row J+1 goes on to form the NEXT diagonal block while the
+            // others work on column J (look-ahead), publishes W_{J+1}, z_{J+1} and the column's partial sums through
+            // global scratch, and comes back for more rows.  Every block is computed by exactly one CTA with the same
+            // arithmetic as in the one-CTA kernel, and the sums are added in column order: bitwise the same result.
+            double* const wg = prm.wg + (size_t)slot * prm.wg_stride;             // 2 x [W | z], then qcol[], lcol[]
+            double* const qcol = wg + 2 * (W_DOUBLES + BS);
+            double* const lcol = qcol + prm.tcap;
+            int* const ctr = prm.cctr + (size_t)slot * (prm.tcap + 2);            // [0] failure flag, [1 + J] row counters
+            auto publish_w = [&](const int buf) {
+                double* dst = wg + (size_t)buf * (W_DOUBLES + BS);
+                for (int i = tid; i < W_DOUBLES / 2; i += NT) reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(sm.W)[i];
+                if (tid < BS) dst[W_DOUBLES + tid] = sm.zs[tid];
+            };
+            auto fetch_w = [&](const int buf) {
+                const double* src = wg + (size_t)buf * (W_DOUBLES + BS);
+                for (int i = tid; i < W_DOUBLES / 2; i += NT) reinterpret_cast<double2*>(sm.W)[i] = __ldcg(reinterpret_cast<const double2*>(src) + i);
+                if (tid < BS) sm.zs[tid] = __ldcg(src + W_DOUBLES + tid);
+            };
+            // column 0: every CTA forms the first diagonal block itself (no accumulate, nothing to wait for)
+            stage_points(sm.colv, vt, prm.npad_max, 0, tid);
+            stage_points(sm.rowv, vt, prm.npad_max, 0, tid);
+            __syncthreads();
+            if (!diag_block(0, -1)) failed = true;
+            if (!failed && crank == 0) {
+                if (tid == 0) column_sums(qcol[0], lcol[0]);
+                publish_w(0);
+            }
+            __threadfence();
+            cluster_sync();
+            for (int J = 0; J < T && !failed; J++) {
+                if (J > 0) {
+                    if (__ldcg(ctr) != 0) { failed = true; break; }           // a pivot of column J failed (same answer in every CTA)
+                    fetch_w(J & 1);
+                    stage_points(sm.colv, vt, prm.npad_max, J, tid);
+                    __syncthreads();
+                }
+                for (;;) {
+                    if (tid == 0) sm.prob2 = atomicAdd(ctr + 1 + J, 1);
+                    __syncthreads();
+                    const int I = J + 1 + sm.prob2;
+                    if (I >= T) break;
+                    offdiag_block(I, J, -1, false);
+                    if (I == J + 1) {
+                        __threadfence();                                       // L_{J+1,J} and ytilde_{J+1} before this CTA's own TMA reads
+                        fence_async();
+                        __syncthreads();
+                        stage_points(sm.colv, vt, prm.npad_max, J + 1, tid);
+                        stage_points(sm.rowv, vt, prm.npad_max, J + 1, tid);
+                        __syncthreads();
+                        const bool ok = diag_block(J + 1, -1);
+                        if (ok) {
+                            if (tid == 0) column_sums(qcol[J + 1], lcol[J + 1]);
+                            publish_w((J + 1) & 1);
+                        } else if (tid == 0) {
+                            atomicExch(ctr, 1);
+                            sm.fail = 0;
+                        }
+                        __syncthreads();
+                        if (J + 2 < T) {                                       // back to column J: its W, z and column points
+                            fetch_w(J & 1);
+                            stage_points(sm.colv, vt, prm.npad_max, J, tid);
+                        }
+                    }
+                    __syncthreads();
+                }
+                __threadfence();
+                fence_async();
+                cluster_sync();
+                fence_async();
+                TICK(11);
+            }
+            if (tid == 0 && crank == 0 && !failed) {
+                for (int J = 0; J < T; J++) { quad += __ldcg(qcol + J); logdet += __ldcg(lcol + J); }
+            }
         }
         if (tid == 0 && crank == 0) {
             double lnl;

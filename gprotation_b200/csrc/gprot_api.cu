@@ -48,6 +48,7 @@ struct gprot_ctx {
     // work-slot scratch
     double* d_lscratch = nullptr; size_t lslot_stride = 0; int lslots = 0;
     double* d_vscratch = nullptr; int v_npad = 0; int vslots = 0;
+    double* d_wg = nullptr; int* d_cctr = nullptr; int cslots = 0;      // cluster kernels: W exchange + row counters
     // problem-list cache (same B, all rows on one light curve, no mask)
     long long cache_B = -1; int cache_lc = -1; int cache_nprob = 0; int cache_tmax = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -149,15 +150,17 @@ kernel_fn kernel_for(bool exact, int cl) {
 }
 
 // Relative time of one problem of T block columns on a cluster of cl CTAs, in units of one 128^3 DMMA block product
-// (weights from the phase budget in DESIGN.md section 4): the diagonal block of a column is formed by every CTA,
-// the T-1-J blocks below it are dealt round-robin.
+// (weights from the phase budget in DESIGN.md section 4, fitted to profiles/r01_cluster_sweep.log): the work is shared,
+// each column loses about half a block row to the granularity of the row queue, and pays a cluster barrier plus the
+// fetch of W.
 double problem_time_model(int T, int cl) {
-    double t = 0.0;
+    double total = 0.0, gran = 0.0;
     for (int J = 0; J < T; J++) {
-        const int rows = T - 1 - J;
-        t += 0.6 * J + 4.0 + (double)((rows + cl - 1) / cl) * (J + 2.0) + (cl > 1 ? 0.05 : 0.0);
+        total += 0.6 * J + 4.0 + (double)(T - 1 - J) * (J + 2.0);
+        if (J < T - 1) gran += J + 2.0;
     }
-    return t;
+    if (cl == 1) return total;
+    return total / cl + gran * (cl - 1) / (2.0 * cl) + T * 0.75 * cl;
 }
 
 int query_clusters(gprot_ctx* ctx) {
@@ -187,7 +190,7 @@ int choose_cluster(gprot_ctx* ctx, int nprob, int tmax) {
     if (tmax < 3) return 1;
     int best = 1;
     double best_t = 0.0;
-    for (int cl : {1, 2, 4, 8}) {
+    for (int cl : {1, 2, 4}) {                               // 8 never wins (too few block rows per column); it can be forced
         const int nc = ctx->max_clusters[cl];
         if (nc <= 0) continue;
         const double rounds = (double)((nprob + nc - 1) / nc);
@@ -314,7 +317,23 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
             ctx->v_npad = np2;
             ctx->vslots = want;
         }
+        constexpr int TCAP = 1024;                                   // block columns (N <= 131072)
+        const size_t wg_stride = 2 * (size_t)(W_DOUBLES + BS) + 2 * TCAP;
+        if (cl > 1) {
+            if (tmax > TCAP) return fail(ctx, "problem too large for the cluster kernels");
+            if (slots > ctx->cslots) {
+                CU(ctx, cudaDeviceSynchronize());
+                if (ctx->d_wg) CU(ctx, cudaFree(ctx->d_wg));
+                if (ctx->d_cctr) CU(ctx, cudaFree(ctx->d_cctr));
+                ctx->d_wg = nullptr; ctx->d_cctr = nullptr;
+                const int want = std::max(slots, ctx->num_sms / 2);
+                CU(ctx, cudaMalloc((void**)&ctx->d_wg, (size_t)want * wg_stride * 8));
+                CU(ctx, cudaMalloc((void**)&ctx->d_cctr, (size_t)want * (TCAP + 2) * 4));
+                ctx->cslots = want;
+            }
+        }
         Params prm;
+        prm.wg = ctx->d_wg; prm.wg_stride = wg_stride; prm.cctr = ctx->d_cctr; prm.tcap = TCAP;
         prm.t = ctx->d_t; prm.y = ctx->d_y; prm.yerr = ctx->d_yerr;
         prm.chunk_off = ctx->d_chunk_off; prm.chunk_n = ctx->d_chunk_n; prm.chunk_mingap2 = ctx->d_chunk_mingap2;
         prm.theta = d_theta;
@@ -397,7 +416,7 @@ int gprot_destroy(gprot_ctx* ctx) {
     cudaDeviceSynchronize();
     void* ptrs[] = {ctx->d_t, ctx->d_y, ctx->d_yerr, ctx->d_chunk_mingap2, ctx->d_chunk_off, ctx->d_chunk_n, ctx->d_theta,
                     ctx->d_out, ctx->d_prob_theta, ctx->d_prob_chunk, ctx->d_prob_out, ctx->d_row_first, ctx->d_row_count,
-                    ctx->d_counter, ctx->d_lscratch, ctx->d_vscratch, ctx->d_timing};
+                    ctx->d_counter, ctx->d_lscratch, ctx->d_vscratch, ctx->d_timing, ctx->d_wg, ctx->d_cctr};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
