@@ -25,10 +25,7 @@
 #include <float.h>
 
 #ifndef PIVOT_VARIANT
-#define PIVOT_VARIANT 1
-#endif
-#ifndef ROWS_VARIANT
-#define ROWS_VARIANT 1
+#define PIVOT_VARIANT 1   // 1: all-lane pivot tile (tile8_factor_all), 0: lane-distributed (tile8_factor); tools/tile8_bench.cu compares them
 #endif
 namespace gprot {
 
@@ -496,87 +493,6 @@ __device__ __forceinline__ void tile8_factor_all(Smem& sm, int p, int buf, int l
     if (bad && lane == 0) sm.fail = 1;
 }
 
-// one rank-8 update task of step p: tile (R, C) -= X(R) * L(C, p)^T
-__device__ __forceinline__ void tile8_update(Smem& sm, int p, int R, int C, int g, int q) {
-    double* M = sm.regionA;
-    const int P0 = 8 * p;
-    double a0, a1;
-    if (R == p) {                                           // rows of the diagonal tile act through W_pp^T
-        const double* wt = sm.wt + 64 * (p & 1);
-        a0 = wt[q * 8 + g];
-        a1 = wt[(q + 4) * 8 + g];
-    } else {
-        const double* ar = M + (8 * R + g) * LDM + P0;
-        a0 = ar[q];
-        a1 = ar[q + 4];
-    }
-    const double* br = M + (8 * C + g) * LDM + P0;
-    const double b0 = br[q], b1 = br[q + 4];
-    double2* cp = reinterpret_cast<double2*>(M + (8 * R + g) * LDM + 8 * C + 2 * q);
-    double2 c = *cp;
-    dmma(c.x, c.y, -a0, b0);
-    dmma(c.x, c.y, -a1, b1);
-    *cp = c;
-}
-
-__device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, long long* tim_, long long& tlast_) {
-    const int g = lane >> 2, q = lane & 3;
-    const int tid = threadIdx.x;
-    (void)tid; (void)tim_; (void)tlast_;
-    double* M = sm.regionA;
-    if (warp == 0) tile8_factor(sm, 0, 0, lane);
-    TICK(12);
-    __syncthreads();
-    for (int p = 0; p < 16; p++) {
-        const int P0 = 8 * p;
-        // (ii) tile row `warp` of the panel: X = M(warp, p) * W_pp^T
-        if (warp != p) {
-            const double* wt = sm.wt + 64 * (p & 1);
-            double* row = M + (8 * warp + g) * LDM + P0;
-            const double a0 = row[q], a1 = row[q + 4];
-            const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
-            double c0 = 0.0, c1 = 0.0;
-            dmma(c0, c1, a0, b0);
-            dmma(c0, c1, a1, b1);
-            __syncwarp();
-            *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
-        }
-        __syncthreads();
-        TICK(13);
-        if (p == 15) break;
-        // (iii) rank-8 update of tiles (R, C), C > p, R in [0..p] (inverse rows) or [C..15] (Schur complement).
-        // Warp 0 updates the next diagonal tile first and factors it right away (look-ahead): the 8 x 8
-        // elimination is the critical path of the sweep, the other 15 warps share the remaining tiles.
-        const int ncol = 15 - p;
-        const int nrect = (p + 1) * ncol;
-        const int ntask = nrect + ncol * (ncol + 1) / 2;
-        if (warp == 0) {
-            tile8_update(sm, p, p + 1, p + 1, g, q);
-            __syncwarp();
-            tile8_factor(sm, p + 1, (p + 1) & 1, lane);
-        } else {
-            for (int task = warp - 1; task < ntask - 1; task += 15) {
-                const int tk = task < nrect ? task : task + 1;   // skip task nrect = tile (p+1, p+1)
-                int R, C;
-                if (tk < nrect) {
-                    R = tk / ncol;
-                    C = p + 1 + tk % ncol;
-                } else {
-                    const int u = tk - nrect;
-                    int i = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
-                    while ((i + 1) * (i + 2) / 2 <= u) i++;
-                    while (i * (i + 1) / 2 > u) i--;
-                    R = p + 1 + i;
-                    C = p + 1 + (u - i * (i + 1) / 2);
-                }
-                tile8_update(sm, p, R, C, g, q);
-            }
-        }
-        TICK(14);
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------- diagonal block, trailing tiles in registers
 // Same elimination as diag_factor (bitwise the same L and W), organised so that the rank-8 updates never touch shared
 // memory: warp R owns tile row R of the workspace (8 rows x 128 columns) and keeps its not-yet-eliminated tiles
@@ -591,7 +507,6 @@ __device__ __forceinline__ void diag_factor(Smem& sm, int warp, int lane, long l
 template <int P>
 __device__ __forceinline__ void rows_update(double (&rt)[16][2], const double* __restrict__ bcol, double* myrow, double a0,
                                             double a1, int chi, int q) {
-#if ROWS_VARIANT == 1
 #pragma unroll
     for (int C = P + 2; C < 16; C++) {
         if (C <= chi) {
@@ -601,30 +516,6 @@ __device__ __forceinline__ void rows_update(double (&rt)[16][2], const double* _
             if (C == P + 2) *reinterpret_cast<double2*>(myrow + 8 * C + 2 * q) = make_double2(rt[C][0], rt[C][1]);
         }
     }
-#else
-#pragma unroll
-    for (int C0 = P + 2; C0 < 16; C0 += 4) {
-        double b0[4], b1[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int C = C0 + u;
-            if (C < 16 && C <= chi) { b0[u] = bcol[(8 * C) * LDM + q]; b1[u] = bcol[(8 * C) * LDM + q + 4]; }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int C = C0 + u;
-            if (C < 16 && C <= chi) dmma(rt[C][0], rt[C][1], a0, b0[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int C = C0 + u;
-            if (C < 16 && C <= chi) {
-                dmma(rt[C][0], rt[C][1], a1, b1[u]);
-                if (C == P + 2) *reinterpret_cast<double2*>(myrow + 8 * C + 2 * q) = make_double2(rt[C][0], rt[C][1]);
-            }
-        }
-    }
-#endif
 }
 
 #ifdef DIAG_TS
@@ -750,7 +641,6 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
                 *reinterpret_cast<double2*>(cp) = x;
             }
         } else {
-#ifndef NO_SWITCH
             switch (p) {
                 case 0: rows_update<0>(rt, bcol, myrow, a0, a1, chi, q); break;
                 case 1: rows_update<1>(rt, bcol, myrow, a0, a1, chi, q); break;
@@ -768,7 +658,6 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
                 case 13: rows_update<13>(rt, bcol, myrow, a0, a1, chi, q); break;
                 default: break;
             }
-#endif
         }
         __syncthreads();                                       // next panel column and its pivot tile are in place
     }
