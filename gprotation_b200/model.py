@@ -222,7 +222,13 @@ class GPRotModel(object):
         return {'A': A, 'metric': l, 'gamma': G, 'white': sigma, 'period': P}
 
     def lnlike_function(self, theta, x, y, yerr):
-        key = (id(x), len(x))
+        # ad-hoc arrays are registered once per content (a digest, not id(): ids are reused after garbage collection)
+        import hashlib
+
+        h = hashlib.blake2b(digest_size=16)
+        for a in (x, y, yerr):
+            h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        key = h.digest()
         lc_id = self._adhoc.get(key)
         if lc_id is None:
             lc_id = self.engine.register_lc(x, y, yerr)
