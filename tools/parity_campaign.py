@@ -1,0 +1,65 @@
+"""Randomised parity campaign on the GPU box: CUDA path (through the C ABI) vs the oracle over random sizes, chunkings,
+light curves and prior draws.  Prints a JSON summary (error percentiles, worst cases, error against condition number)
+and writes it to gpurun_out/parity_campaign.json.  usage: python tools/parity_campaign.py [ncases] [seed]"""
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import gp_oracle as o  # noqa: E402
+from gprotation_b200 import GPEngine  # noqa: E402
+from gprotation_b200.synth import synthetic_lightcurve  # noqa: E402
+
+ncases = int(sys.argv[1]) if len(sys.argv) > 1 else 120
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+rng = np.random.default_rng(seed)
+eng = GPEngine(0)
+rows = []
+t0 = time.time()
+for case in range(ncases):
+    n = int(rng.choice([rng.integers(1, 130), rng.integers(130, 700), rng.integers(700, 1600)]))
+    kind = "gp" if (n <= 600 and rng.random() < 0.5) else "harmonic"
+    t, y, yerr, truth = synthetic_lightcurve(int(rng.integers(1 << 30)), n, baseline=float(rng.uniform(0.3, 3.0)) * max(n, 40), kind=kind)
+    if rng.random() < 0.3:
+        yerr = yerr * rng.uniform(0.5, 20.0, size=n)          # heteroscedastic errors
+    cs = None if rng.random() < 0.5 else int(rng.integers(max(2, n // 8), n + 1))
+    chunks = o.split_chunks(n, cs)
+    eng.unregister_all()
+    lc = eng.register_lc(t, y, yerr, chunks=chunks)
+    th = o.sample_from_prior(5, seed=int(rng.integers(1 << 30)))
+    th[0] = truth
+    cl = int(rng.choice([0, 1, 2, 4]))
+    eng.set_cluster(cl)
+    for exact in (False, True):
+        got = eng.lnlike_batch(th, lc_id=lc, exact=exact)
+        for k, x in enumerate(th):
+            ref = o.lnlike(x, t, y, yerr, chunks)
+            if chunks is None:
+                K = o.kernel_matrix(x, t, yerr)
+                ev = np.linalg.eigvalsh(K)
+                cond = float(ev[-1] / ev[0]) if ev[0] > 0 else float("inf")
+                terms = 0.5 * (abs(float(np.sum(np.log(np.abs(ev))))) + n * math.log(2 * math.pi))
+            else:
+                cond, terms = float("nan"), float("nan")
+            rows.append(dict(n=n, chunksize=cs, kind=kind, cluster=cl, exact=exact, ref=float(ref), got=float(got[k]), cond=cond, terms=terms))
+eng.set_cluster(0)
+fin = [r for r in rows if math.isfinite(r["ref"])]
+rel = np.array([abs(r["got"] - r["ref"]) / abs(r["ref"]) for r in fin])
+mism = [r for r in rows if math.isfinite(r["ref"]) != math.isfinite(r["got"])]
+worst = sorted(fin, key=lambda r: -abs(r["got"] - r["ref"]) / abs(r["ref"]))[:8]
+summary = {
+    "cases": ncases, "evaluations": len(rows), "finite": len(fin), "minus_inf_in_both": len(rows) - len(fin) - len(mism),
+    "finiteness_mismatches": len(mism), "seconds": time.time() - t0,
+    "rel_err_percentiles": {str(p): float(np.percentile(rel, p)) for p in (50, 90, 99, 100)},
+    "fraction_within_1e-9": float(np.mean(rel <= 1e-9)), "fraction_within_1e-10": float(np.mean(rel <= 1e-10)),
+    "worst": [dict(n=r["n"], chunksize=r["chunksize"], cluster=r["cluster"], exact=r["exact"], cond=r["cond"], ref=r["ref"],
+                   rel_err=abs(r["got"] - r["ref"]) / abs(r["ref"]),
+                   err_over_terms=(abs(r["got"] - r["ref"]) / r["terms"]) if r["terms"] == r["terms"] else None) for r in worst],
+}
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(summary, open("gpurun_out/parity_campaign.json", "w"), indent=1)
+print(json.dumps(summary, indent=1))
