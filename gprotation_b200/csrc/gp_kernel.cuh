@@ -1095,6 +1095,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
 #endif
 }
 
+#ifdef GPROT_API_TU   // small non-template kernels: compiled once, in the translation unit of the C ABI
 // out[b] = sum over the row's problems, in a fixed order (gprot/model.py:362-365 np.sum over chunks)
 __global__ void reduce_rows_kernel(const double* __restrict__ prob_out, const int* __restrict__ row_first,
                                    const int* __restrict__ row_count, double* __restrict__ out, long long B) {
@@ -1129,5 +1130,7 @@ __global__ void dmma_peak_kernel(double* out, int iters, long long* cyc) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
 }
+
+#endif
 
 }  // namespace gprot

@@ -2,7 +2,16 @@
 // Host side of the boundary: light-curve arena, problem queue, work-slot scratch, launches.
 // No CPU fallback: every numeric result comes from gp_lnlike_kernel.
 #include "../../include/gprot_b200.h"
+#define GPROT_API_TU
 #include "gp_kernel.cuh"
+
+// the likelihood kernels are instantiated in gp_kernel_inst.cu (one object per variant, built in parallel)
+namespace gprot {
+#define GPROT_EXTERN_KERNEL(E, C) extern template __global__ void gp_lnlike_kernel<E, C>(const Params);
+GPROT_EXTERN_KERNEL(false, 1) GPROT_EXTERN_KERNEL(false, 2) GPROT_EXTERN_KERNEL(false, 4) GPROT_EXTERN_KERNEL(false, 8)
+GPROT_EXTERN_KERNEL(true, 1) GPROT_EXTERN_KERNEL(true, 2) GPROT_EXTERN_KERNEL(true, 4) GPROT_EXTERN_KERNEL(true, 8)
+#undef GPROT_EXTERN_KERNEL
+}  // namespace gprot
 
 #include <algorithm>
 #include <cmath>
