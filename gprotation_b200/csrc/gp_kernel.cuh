@@ -77,6 +77,7 @@ struct Params {
     const int* prob_theta;        // [nprob] row of theta
     const int* prob_chunk;        // [nprob] chunk index
     double* prob_out;             // [nprob]
+    const int* prob_order;        // [nprob] queue order (largest problems first) or nullptr = as listed
     int nprob;
     int* counter;                 // work queue head
     double* lscratch;             // per-slot factor scratch
@@ -759,8 +760,8 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             sm.fail = 0;
         }
         if (CL > 1) cluster_sync(); else __syncthreads();
-        const int prob = sm.prob;
-        if (prob >= prm.nprob) break;
+        if (sm.prob >= prm.nprob) break;
+        const int prob = prm.prob_order ? prm.prob_order[sm.prob] : sm.prob;
         TICK(15);
 
         const int chunk = prm.prob_chunk[prob];

@@ -49,7 +49,8 @@ struct gprot_ctx {
     // per-call buffers (grown on demand)
     double* d_theta = nullptr; size_t cap_theta = 0;
     double* d_out = nullptr; size_t cap_out = 0;
-    int *d_prob_theta = nullptr, *d_prob_chunk = nullptr; size_t cap_prob = 0;
+    int *d_prob_theta = nullptr, *d_prob_chunk = nullptr, *d_prob_order = nullptr; size_t cap_prob = 0;
+    bool use_order = false;           // the last problem list has mixed sizes and is queued largest first
     double* d_prob_out = nullptr;
     int *d_row_first = nullptr, *d_row_count = nullptr; size_t cap_rows = 0;
     int* d_counter = nullptr;
@@ -255,11 +256,13 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
             if (ctx->d_prob_theta) cudaFree(ctx->d_prob_theta);
             if (ctx->d_prob_chunk) cudaFree(ctx->d_prob_chunk);
             if (ctx->d_prob_out) cudaFree(ctx->d_prob_out);
-            ctx->d_prob_theta = ctx->d_prob_chunk = nullptr; ctx->d_prob_out = nullptr;
+            if (ctx->d_prob_order) cudaFree(ctx->d_prob_order);
+            ctx->d_prob_theta = ctx->d_prob_chunk = ctx->d_prob_order = nullptr; ctx->d_prob_out = nullptr;
             const size_t c = std::max<size_t>(nprob, ctx->cap_prob * 2);
             CU(ctx, cudaMalloc((void**)&ctx->d_prob_theta, c * 4));
             CU(ctx, cudaMalloc((void**)&ctx->d_prob_chunk, c * 4));
             CU(ctx, cudaMalloc((void**)&ctx->d_prob_out, c * 8));
+            CU(ctx, cudaMalloc((void**)&ctx->d_prob_order, c * 4));
             ctx->cap_prob = c;
         }
         CU(ctx, cudaMemcpyAsync(ctx->d_row_first, rfirst.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
@@ -267,6 +270,21 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
         if (nprob > 0) {
             CU(ctx, cudaMemcpyAsync(ctx->d_prob_theta, ptheta.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
             CU(ctx, cudaMemcpyAsync(ctx->d_prob_chunk, pchunk.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
+        }
+        // Mixed problem sizes: the persistent CTAs take the largest problems first (longest-processing-time-first), so
+        // that a big problem is never the last one popped.  Outputs keep their listed positions.
+        std::vector<int> order;
+        ctx->use_order = false;
+        if (nprob > 1) {
+            int nmin = ctx->h_chunk_n[pchunk[0]], nmax = nmin;
+            for (int k = 1; k < nprob; k++) { const int v = ctx->h_chunk_n[pchunk[k]]; nmin = std::min(nmin, v); nmax = std::max(nmax, v); }
+            if ((nmax + BS - 1) / BS != (nmin + BS - 1) / BS) {
+                order.resize((size_t)nprob);
+                for (int k = 0; k < nprob; k++) order[k] = k;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->h_chunk_n[pchunk[a]] > ctx->h_chunk_n[pchunk[b]]; });
+                CU(ctx, cudaMemcpyAsync(ctx->d_prob_order, order.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
+                ctx->use_order = true;
+            }
         }
         CU(ctx, cudaStreamSynchronize(st));   // the host vectors go out of scope
         if (cacheable) { ctx->cache_B = B; ctx->cache_lc = 0; ctx->cache_nprob = nprob; ctx->cache_tmax = tmax; }
@@ -347,6 +365,7 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
         prm.chunk_off = ctx->d_chunk_off; prm.chunk_n = ctx->d_chunk_n; prm.chunk_mingap2 = ctx->d_chunk_mingap2;
         prm.theta = d_theta;
         prm.prob_theta = ctx->d_prob_theta; prm.prob_chunk = ctx->d_prob_chunk; prm.prob_out = ctx->d_prob_out;
+        prm.prob_order = ctx->use_order ? ctx->d_prob_order : nullptr;
         prm.nprob = nprob;
         prm.counter = ctx->d_counter;
         prm.lscratch = ctx->d_lscratch; prm.lslot_stride = ctx->lslot_stride;
@@ -424,7 +443,7 @@ int gprot_destroy(gprot_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void* ptrs[] = {ctx->d_t, ctx->d_y, ctx->d_yerr, ctx->d_chunk_mingap2, ctx->d_chunk_off, ctx->d_chunk_n, ctx->d_theta,
-                    ctx->d_out, ctx->d_prob_theta, ctx->d_prob_chunk, ctx->d_prob_out, ctx->d_row_first, ctx->d_row_count,
+                    ctx->d_out, ctx->d_prob_theta, ctx->d_prob_chunk, ctx->d_prob_order, ctx->d_prob_out, ctx->d_row_first, ctx->d_row_count,
                     ctx->d_counter, ctx->d_lscratch, ctx->d_vscratch, ctx->d_timing, ctx->d_wg, ctx->d_cctr};
     for (void* p : ptrs)
         if (p) cudaFree(p);

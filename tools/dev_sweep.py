@@ -108,3 +108,16 @@ if "cl" in cases:
                     base = got
                 assert np.array_equal(got, base)
     eng.set_cluster(0)
+
+if "mixed" in cases:
+    # adverse order: many small problems first, a few large ones last (largest-first queueing should hide the tail)
+    eng.unregister_all()
+    t, y, yerr, _ = synthetic_lightcurve(6, 300, kind="harmonic")
+    small = eng.register_lc(t, y, yerr)
+    t2, y2, yerr2, _ = synthetic_lightcurve(7, 2048, kind="harmonic")
+    big = eng.register_lc(t2, y2, yerr2)
+    th = o.sample_from_prior(3000 + 40, seed=11)
+    ids = np.array([small] * 3000 + [big] * 40, dtype=np.int32)
+    F = (3000 * o.flops_per_eval(300) + 40 * o.flops_per_eval(2048)) / len(th)
+    run("mixed 3000 x N=300 then 40 x N=2048", th, ids, 1, F)
+    run("same, large ones listed first", th[::-1].copy(), ids[::-1].copy(), 1, F)
