@@ -161,14 +161,14 @@ __device__ __forceinline__ int w_off(int c, int m) {
 // Store a warp's 32 x 32 C-fragment tile (acc[mi][ni][e] at row 8mi+g, col 8ni+2q+e) into a fragment-major
 // block at tile origin (row0, col0), optionally negated.  Lanes q and q^2 hold neighbouring doubles of the
 // destination, so one shuffle turns 32 scalar stores into 16 16-byte stores.
-template <bool NEG>
+template <bool NEG, int SLABSTRIDE = SLAB>
 __device__ __forceinline__ void store_tile_frag(double* blk, const double (&acc)[4][4][2], int row0, int col0, int lane) {
     const int g = lane >> 2, q = lane & 3, h = q >> 1;
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) {
         const int c = col0 + 8 * ni;                       // multiple of 8
         const int slab = c >> 4, kp = (c >> 3) & 1;
-        double* base = blk + slab * SLAB + kp * 64 + ((g << 2) + ((q & 1) << 1) + h) * 2;
+        double* base = blk + slab * SLABSTRIDE + kp * 64 + ((g << 2) + ((q & 1) << 1) + h) * 2;
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
             double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
@@ -253,8 +253,8 @@ __device__ __forceinline__ double neg_kentry(double ti, double tj, double si, do
 // sm.colv: block column).  rl0 / cl0 = first row / column of the warp tile inside the block, row0 / col0 the same in
 // the problem.  GENERAL handles the diagonal (white noise + yerr), identity padding beyond n, and coincident time
 // stamps off the diagonal.
-template <bool EXACT, bool GENERAL>
-__device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], const Smem& sm, int rl0, int cl0, int row0, int col0, int n,
+template <bool EXACT, bool GENERAL, int RSTRIDE = BS, int CSTRIDE = BS, class SM = Smem>
+__device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], const SM& sm, int rl0, int cl0, int row0, int col0, int n,
                                            const double* vd, bool white_off, int lane) {
     const int g = lane >> 2, q = lane & 3;
     const Hyp& h = sm.hyp;
@@ -263,15 +263,15 @@ __device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], const Smem& s
     for (int mi = 0; mi < 4; mi++) {
         const int r = rl0 + 8 * mi + g;
         ti[mi] = sm.rowv[r];
-        si[mi] = sm.rowv[BS + r];
-        ci[mi] = sm.rowv[2 * BS + r];
+        si[mi] = sm.rowv[RSTRIDE + r];
+        ci[mi] = sm.rowv[2 * RSTRIDE + r];
     }
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) {
         const int cl = cl0 + 8 * ni + 2 * q;
         const double2 tj2 = *reinterpret_cast<const double2*>(sm.colv + cl);
-        const double2 sj2 = *reinterpret_cast<const double2*>(sm.colv + BS + cl);
-        const double2 cj2 = *reinterpret_cast<const double2*>(sm.colv + 2 * BS + cl);
+        const double2 sj2 = *reinterpret_cast<const double2*>(sm.colv + CSTRIDE + cl);
+        const double2 cj2 = *reinterpret_cast<const double2*>(sm.colv + 2 * CSTRIDE + cl);
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const double tj = e ? tj2.y : tj2.x, sj = e ? sj2.y : sj2.x, cj = e ? cj2.y : cj2.x;

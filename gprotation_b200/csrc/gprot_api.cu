@@ -4,6 +4,7 @@
 #include "../../include/gprot_b200.h"
 #define GPROT_API_TU
 #include "gp_kernel.cuh"
+#include "gp_kernel64.cuh"
 
 // the likelihood kernels are instantiated in gp_kernel_inst.cu (one object per variant, built in parallel)
 namespace gprot {
@@ -11,11 +12,16 @@ namespace gprot {
 GPROT_EXTERN_KERNEL(false, 1) GPROT_EXTERN_KERNEL(false, 2) GPROT_EXTERN_KERNEL(false, 4) GPROT_EXTERN_KERNEL(false, 8)
 GPROT_EXTERN_KERNEL(true, 1) GPROT_EXTERN_KERNEL(true, 2) GPROT_EXTERN_KERNEL(true, 4) GPROT_EXTERN_KERNEL(true, 8)
 #undef GPROT_EXTERN_KERNEL
+namespace k64 {
+extern template __global__ void gp_lnlike64_kernel<false>(const Params);
+extern template __global__ void gp_lnlike64_kernel<true>(const Params);
+}
 }  // namespace gprot
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -65,7 +71,9 @@ struct gprot_ctx {
     float last_ms = 0.f;
     int64_t launches = 0;
     bool attr_set = false;
-    int force_cluster = 0;            // 0 = choose per launch; 1, 2, 4, 8 = CTAs per problem
+    int force_cluster = 0;            // 0 = choose per launch; 1, 2, 4, 8 = CTAs per problem; 64 = two problems per SM
+    bool attr64_set = false;
+    int last_nmax = 0;                // largest chunk of the cached problem list
     int max_clusters[9] = {0};        // co-resident clusters of each size (cudaOccupancyMaxActiveClusters), 0 = unknown
     int last_cluster = 1;
 };
@@ -196,6 +204,7 @@ int query_clusters(gprot_ctx* ctx) {
 // CTAs per problem for a launch of nprob problems whose largest has tmax block columns: the size that minimises
 // rounds x modelled time per problem.  Batches that fill the GPU (nprob >= SMs) with short tails stay at 1.
 int choose_cluster(gprot_ctx* ctx, int nprob, int tmax) {
+    if (ctx->force_cluster == 64) return 1;
     if (ctx->force_cluster) return ctx->max_clusters[ctx->force_cluster] > 0 ? ctx->force_cluster : 1;
     if (tmax < 3) return 1;
     int best = 1;
@@ -222,10 +231,11 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
 
     // ---- problem list
     const bool cacheable = (lc_id == nullptr && mask == nullptr);
-    int nprob = 0, tmax = 0;
+    int nprob = 0, tmax = 0, nmax = 0;
     if (cacheable && ctx->cache_B == B && ctx->cache_lc == 0) {
         nprob = ctx->cache_nprob;
         tmax = ctx->cache_tmax;
+        nmax = ctx->last_nmax;
     } else {
         std::vector<int> ptheta, pchunk, rfirst((size_t)B), rcount((size_t)B);
         const int nlc = (int)ctx->lc_first_chunk.size();
@@ -240,6 +250,7 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
                 ptheta.push_back((int)b);
                 pchunk.push_back(f + c);
                 tmax = std::max(tmax, (ctx->h_chunk_n[f + c] + BS - 1) / BS);
+                nmax = std::max(nmax, ctx->h_chunk_n[f + c]);
             }
         }
         nprob = (int)ptheta.size();
@@ -287,6 +298,7 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
             }
         }
         CU(ctx, cudaStreamSynchronize(st));   // the host vectors go out of scope
+        ctx->last_nmax = nmax;
         if (cacheable) { ctx->cache_B = B; ctx->cache_lc = 0; ctx->cache_nprob = nprob; ctx->cache_tmax = tmax; }
         else ctx->cache_B = -1;
     }
@@ -313,11 +325,31 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
             ctx->attr_set = true;
         }
         query_clusters(ctx);
-        const int cl = choose_cluster(ctx, nprob, tmax);
-        ctx->last_cluster = cl;
-        int slots = std::min(nprob, ctx->max_clusters[cl]);      // one slot per co-resident CTA group
-        const size_t stride = std::max<size_t>((size_t)tmax * (tmax - 1) / 2, 1) * BLKD;
-        const int npad = tmax * BS;
+        int cl = choose_cluster(ctx, nprob, tmax);
+        // Launches with at least two problems per SM run the two-problems-per-SM kernel (gp_kernel64.cuh); smaller ones
+        // keep one problem per SM (or per cluster).  gprot_set_cluster(64) / (1) force either.
+        const bool use64 = ctx->force_cluster == 64 ||
+                           (ctx->force_cluster == 0 && cl == 1 && nprob > ctx->num_sms && nmax < 1920);   // measured crossover
+        if (use64) cl = 1;
+        ctx->last_cluster = use64 ? 64 : cl;
+        if (use64 && !ctx->attr64_set) {
+            for (int ex = 0; ex < 2; ex++) {
+                const void* f = ex ? (const void*)k64::gp_lnlike64_kernel<true> : (const void*)k64::gp_lnlike64_kernel<false>;
+                CU(ctx, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k64::Smem2)));
+                CU(ctx, cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
+            ctx->attr64_set = true;
+            if (getenv("GPROT_DEBUG")) {
+                int nb = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k64::gp_lnlike64_kernel<false>, k64::NT2, sizeof(k64::Smem2));
+                fprintf(stderr, "[gprot] gp_lnlike64_kernel: %d CTAs per SM, %zu bytes of shared memory each\n", nb, sizeof(k64::Smem2));
+            }
+        }
+        const int t64 = (nmax + k64::BC - 1) / k64::BC;
+        int slots = use64 ? std::min(nprob, 2 * ctx->num_sms) : std::min(nprob, ctx->max_clusters[cl]);   // one slot per resident CTA (group)
+        const size_t stride = use64 ? std::max<size_t>((size_t)t64 * (t64 - 1) / 2, 1) * k64::BLK2
+                                    : std::max<size_t>((size_t)tmax * (tmax - 1) / 2, 1) * BLKD;
+        const int npad = use64 ? (t64 + 1) * k64::BC : tmax * BS;        // the 64-wide kernel reads one block past the end
         if (stride > ctx->lslot_stride || slots > ctx->lslots) {
             CU(ctx, cudaDeviceSynchronize());
             if (ctx->d_lscratch) CU(ctx, cudaFree(ctx->d_lscratch));
@@ -373,7 +405,10 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
         prm.timing = ctx->d_timing;
         CU(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
         CU(ctx, cudaEventRecord(ctx->ev0, st));
-        {
+        if (use64) {
+            if (flags & GPROT_EXACT_KERNEL) k64::gp_lnlike64_kernel<true><<<slots, k64::NT2, sizeof(k64::Smem2), st>>>(prm);
+            else                            k64::gp_lnlike64_kernel<false><<<slots, k64::NT2, sizeof(k64::Smem2), st>>>(prm);
+        } else {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(slots * cl));
             cfg.blockDim = dim3(NT);
@@ -544,8 +579,9 @@ int64_t gprot_launch_count(const gprot_ctx* ctx) { return ctx ? ctx->launches : 
 
 int gprot_set_cluster(gprot_ctx* ctx, int ctas_per_problem) {
     if (!ctx) return fail(nullptr, "null context");
-    if (ctas_per_problem != 0 && ctas_per_problem != 1 && ctas_per_problem != 2 && ctas_per_problem != 4 && ctas_per_problem != 8)
-        return fail(ctx, "ctas_per_problem must be 0 (auto), 1, 2, 4 or 8");
+    if (ctas_per_problem != 0 && ctas_per_problem != 1 && ctas_per_problem != 2 && ctas_per_problem != 4 && ctas_per_problem != 8 &&
+        ctas_per_problem != 64)
+        return fail(ctx, "ctas_per_problem must be 0 (auto), 1, 2, 4, 8, or 64 (the two-problems-per-SM kernel)");
     ctx->force_cluster = ctas_per_problem;
     return 0;
 }

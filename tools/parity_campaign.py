@@ -49,7 +49,7 @@ for case in range(ncases):
     lc = eng.register_lc(t, y, yerr, chunks=chunks)
     th = o.sample_from_prior(5, seed=int(rng.integers(1 << 30)))
     th[0] = truth
-    cl = int(rng.choice([0, 1, 2, 4]))
+    cl = int(rng.choice([0, 1, 2, 4, 64]))
     eng.set_cluster(cl)
     for exact in (False, True):
         got = eng.lnlike_batch(th, lc_id=lc, exact=exact)
