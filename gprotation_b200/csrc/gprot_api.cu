@@ -206,7 +206,7 @@ int query_clusters(gprot_ctx* ctx) {
 int choose_cluster(gprot_ctx* ctx, int nprob, int tmax) {
     if (ctx->force_cluster == 64) return 1;
     if (ctx->force_cluster) return ctx->max_clusters[ctx->force_cluster] > 0 ? ctx->force_cluster : 1;
-    if (tmax < 3) return 1;
+    if (tmax < 4) return 1;                                  // measured: three block columns do not pay for the cluster barriers
     int best = 1;
     double best_t = 0.0;
     for (int cl : {1, 2, 4}) {                               // 8 never wins (too few block rows per column); it can be forced
