@@ -141,10 +141,13 @@ class GPEngine(object):
         return ms.value
 
     def set_cluster(self, ctas_per_problem=0):
-        """CTAs per problem: 0 = chosen per launch, or 1 / 2 / 4 / 8 (results are bitwise identical)."""
+        """Kernel choice: 0 = per launch (default); 1 / 2 / 4 / 8 = CTAs per problem of the one-problem-per-SM kernel
+        (bitwise identical results among themselves); 64 = the two-problems-per-SM kernel (64 x 64 blocks; agrees with
+        the others to fp64 rounding, ~eps * cond)."""
         self._check(self._lib.gprot_set_cluster(self._ctx, int(ctas_per_problem)))
 
     def last_cluster(self):
+        """What the last launch used: 1, 2, 4, 8 CTAs per problem, or 64 for the two-problems-per-SM kernel."""
         return int(self._lib.gprot_last_cluster(self._ctx))
 
     def launch_count(self):
