@@ -79,8 +79,8 @@ int gprot_lnpost_batch(gprot_ctx *ctx, int64_t B, const double *theta, const int
 int gprot_sync(gprot_ctx *ctx);
 
 /* Kernel choice.  Launches with more than one problem per SM and N < 1920 run two problems per SM (64 x 64 blocks,
- * gp_kernel64.cuh); larger problems run one per SM (128 x 128 blocks).  A launch with fewer problems than SMs (32 problems per GPU for the
- * N=8192 stress at 8 GPUs; one emcee3 half-ensemble of a single star, gprot/fit.py:98) spreads each problem over a
+ * gp_kernel64.cuh); larger problems run one per SM (128 x 128 blocks).  A launch with fewer problems than SMs
+ * (32 problems per GPU for the N=8192 stress at 8 GPUs; one emcee3 half-ensemble of a single star, gprot/fit.py:98) spreads each problem over a
  * thread-block cluster of 2, 4 or 8 CTAs.  0 (default) chooses per launch from the batch size; results are bitwise
  * identical for 1, 2, 4 and 8.  64 forces the two-problems-per-SM kernel, 1 the one-problem-per-SM kernel (the two
  * blockings agree to fp64 rounding, ~eps * cond(K)).  gprot_last_cluster reports what the last launch used. */
