@@ -71,20 +71,20 @@ def _fit_emcee3(i, **kwargs):
 
 
 def build_parser():
-    parser = argparse.ArgumentParser(description='Fit aigrain simulations or kepler light curves with GP rotation model.')
-    parser.add_argument('stars', nargs='+', type=int, help='Stars to fit.')
+    parser = argparse.ArgumentParser(description='Quasi-periodic GP rotation-period fits of Aigrain simulations or Kepler light curves on the B200 engine.')
+    parser.add_argument('stars', nargs='+', type=int, help='Star ids, fitted one after another.')
     datagroup = parser.add_mutually_exclusive_group()
-    datagroup.add_argument("--aigrain", dest="aigrain", action='store_true', help="Use Aigrain simulations.")
-    datagroup.add_argument("--kepler", dest="kepler", action='store_true', help="Use Kepler data.")
+    datagroup.add_argument("--aigrain", dest="aigrain", action='store_true', help="Read the Aigrain et al. simulation files (AIGRAIN_ROTATION).")
+    datagroup.add_argument("--kepler", dest="kepler", action='store_true', help="Kepler light curves (needs kplr; not available offline).")
     group = parser.add_mutually_exclusive_group()
     group.add_argument("--ncores", dest="n_cores", default=1, type=int,
                        help="Accepted for compatibility: walkers are batched on the GPU, not spread over processes.")
     group.add_argument("--mpi", dest="mpi", default=False, action="store_true", help="Accepted for compatibility (see --ncores).")
     parser.add_argument('--device', default=0, type=int, help='CUDA device ordinal of this process.')
-    parser.add_argument('-v', '--verbose', action='store_true', help='Have the sampler talk to you.')
+    parser.add_argument('-v', '--verbose', action='store_true', help='Print convergence statistics and a progress bar.')
     parser.add_argument('--clever', action='store_true',
-                        help='Subsample in a tiered way but use whole light curve. Supersedes "quarters", "subsample", '
-                             'and "daterange" arguments.')
+                        help='Tiered chunks from the most variable 800/200/50-day windows of the whole light curve; overrides '
+                             '--quarters, --subsample and --daterange.')
     parser.add_argument('--npoints', type=int, default=600)
     parser.add_argument('--acf_prior', action='store_true')
     parser.add_argument('--sap', action='store_true')
@@ -92,26 +92,24 @@ def build_parser():
     parser.add_argument('--bestchunk', nargs='+', type=int, default=None)
     parser.add_argument('--tag', default=None)
     parser.add_argument('--quarters', nargs='+', type=int, default=None)
-    parser.add_argument('--sampler', choices=['mnest', 'emcee3', 'polychord'], default='emcee3', help='Which sampling method to use.')
-    parser.add_argument('--resultsdir', default='results', help='Directory in which to store results.')
-    parser.add_argument('-n', '--ndays', default=None, type=int, help='Number of days (from beginning) of light curve to use for fitting.')
-    parser.add_argument('--subsample', default=30, type=int, help='subsampling factor.')
-    parser.add_argument('--chunksize', default=300, type=int, help='Size (in number of points) of the chunks into which to split light curve.')
-    parser.add_argument('--nwalkers', default=500, type=int, help='Number of walkers (for emcee3)')
-    parser.add_argument('--iter_chunksize', default=50, type=int, help='Number of emcee3 steps after which to check for convergence.')
-    parser.add_argument('--targetn', default=6, type=int, help='Number of autocorrelation times after which to say fit has converged.')
-    parser.add_argument('--nburn', default=2, type=int, help='Number of autocorrelation times to toss out as burn-in.')
-    parser.add_argument('--maxiter', default=50, type=int, help='Maximum number of times to repeat <iter_chunksize> steps of emcee3.')
+    parser.add_argument('--sampler', choices=['mnest', 'emcee3', 'polychord'], default='emcee3', help='Sampler; only emcee3 is available here.')
+    parser.add_argument('--resultsdir', default='results', help='Output directory for samples, light curve and priors.')
+    parser.add_argument('-n', '--ndays', default=None, type=int, help='Use only the first NDAYS days of the light curve.')
+    parser.add_argument('--subsample', default=30, type=int, help='Keep one point in SUBSAMPLE (random, seeded with the star id).')
+    parser.add_argument('--chunksize', default=300, type=int, help='Largest number of points per independent chunk.')
+    parser.add_argument('--nwalkers', default=500, type=int, help='Ensemble size.')
+    parser.add_argument('--iter_chunksize', default=50, type=int, help='Steps per block between convergence checks.')
+    parser.add_argument('--targetn', default=6, type=int, help='Chain length, in autocorrelation times, that counts as converged.')
+    parser.add_argument('--nburn', default=2, type=int, help='Autocorrelation times discarded as burn-in.')
+    parser.add_argument('--maxiter', default=50, type=int, help='Upper limit on the number of blocks.')
     parser.add_argument('-o', '--overwrite', action='store_true',
-                        help='Overwrite existing fit.  If this is not set and a fit has been done/started before, it will '
-                             'restart from previous stopping point.')
-    parser.add_argument('--daterange', nargs=2, type=float, help='Beginning and end of specified date range of fit.')
+                        help='Start from scratch; without it a stored chain of the same star is resumed.')
+    parser.add_argument('--daterange', nargs=2, type=float, help='Restrict the fit to times between the two values.')
     parser.add_argument('--mixedmoves', action='store_true', default=True,
-                        help='If this is set, then a 2:2:1 mix of KDEMove, DEMove and DESnookerMove are used in emcee3 fit. '
-                             'Otherwise, just KDEMove is used.')
-    parser.add_argument('--nlive', default=1000, type=int, help='Number of live points (for multinest)')
-    parser.add_argument('--test', action='store_true', help="Test, don't actually run. Flag has no effect if sampler is set to emcee3.")
-    parser.add_argument('--offline', action='store_true', help='enable offline kplr data access')
+                        help='KDE / differential-evolution / snooker moves in proportion 2:2:1 (default); otherwise KDE only.')
+    parser.add_argument('--nlive', default=1000, type=int, help='Live points (MultiNest only).')
+    parser.add_argument('--test', action='store_true', help="Dry run for the nested samplers; ignored by emcee3.")
+    parser.add_argument('--offline', action='store_true', help='kplr offline mode.')
     parser.add_argument('--altmodel', action='store_true')
     parser.add_argument('--nochunks', action='store_true')
     parser.add_argument('--seed', default=None, type=int, help='Seed of the sampler (not in the reference).')

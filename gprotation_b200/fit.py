@@ -131,101 +131,93 @@ def read_samples(samplefile, key='samples'):
     return pd.read_hdf(samplefile, key)
 
 
+def _chain_store(mod, sample_directory):
+    """Where the chain lives between calls: ``<sample_directory>/<name>.h5`` in the reference (emcee3 HDFBackend,
+    gprot/fit.py:69-72); the sibling .npz here.  ``None`` keeps the chain in memory only."""
+    import os
+
+    from . import sampler as em
+
+    if sample_directory is None:
+        return em.Backend()
+    os.makedirs(sample_directory, exist_ok=True)
+    return em.HDFBackend(os.path.join(sample_directory, '{}.h5'.format(mod.name)))
+
+
+def _starting_coords(mod, store, nwalkers, fresh, seed):
+    """Resume from the last stored ensemble when there is one (gprot/fit.py:73-76), else draw from the prior."""
+    if not fresh:
+        try:
+            return store.current_coords
+        except (AttributeError, KeyError):
+            pass
+    return mod.sample_from_prior(nwalkers, seed=seed)
+
+
+def _chain_length_in_autocorr_times(sampler, nburn, nwalkers, verbose):
+    """(tau_max, chain length in units of tau_max minus the burn-in allowance): the convergence statistic of
+    gprot/fit.py:100-110.  Raises AutocorrError while the chain is too short to tell."""
+    tau_max = sampler.get_integrated_autocorr_time(c=1).max()
+    neff = sampler.backend.niter / tau_max - nburn
+    if verbose:
+        print("Maximum autocorrelation time: {0}".format(tau_max))
+        print("N_eff: {0}\n".format(neff * nwalkers))
+    return tau_max, neff
+
+
 def fit_emcee3(mod, nwalkers=500, verbose=False, nsamples=5000, targetn=6,
                iter_chunksize=10, pool=None, overwrite=False,
                maxiter=100, sample_directory='mcmc_chains',
                nburn=3, mixedmoves=True, resultsdir='results', seed=None, **kwargs):
-    """gprot/fit.py:53-152 with the same arguments and control flow: resume from the stored chain unless
-    ``overwrite``, a 0.4 / 0.4 / 0.2 mixture of KDE, DE(1.0) and DE-snooker moves, blocks of ``iter_chunksize``
-    steps until the chain is ``targetn`` autocorrelation times long, ``nburn`` autocorrelation times discarded,
-    ``nsamples`` random draws written with ``write_samples``.  ``pool`` defaults to ``EnsemblePool``: every
-    half-ensemble proposal set is one device launch (the reference's DefaultPool / schwimmbad pool evaluates one
-    walker per call).  ``seed`` (not in the reference) makes a run reproducible."""
-    import os
-
+    """The reference's fit driver (gprot/fit.py:53-152), same arguments and behaviour: resume from the stored chain
+    unless ``overwrite``; a 0.4 / 0.4 / 0.2 mixture of KDE, DE(1.0) and DE-snooker moves (KDE alone without
+    ``mixedmoves``); blocks of ``iter_chunksize`` steps, at most ``maxiter`` of them, until the chain is ``targetn``
+    autocorrelation times long after ``nburn`` of them are set aside; ``nsamples`` random draws from what is left,
+    written with ``write_samples`` and returned as a DataFrame.  ``pool`` defaults to ``EnsemblePool``: every
+    half-ensemble proposal set is ONE device launch (the reference's DefaultPool / schwimmbad pool evaluates one walker
+    per call).  ``seed`` (not in the reference) makes a run reproducible."""
     import pandas as pd
 
     from . import sampler as em
 
-    walker = Emcee3Model(mod)
     rs = np.random.RandomState(seed)
-
-    if sample_directory is not None:
-        sample_file = os.path.join(sample_directory, '{}.h5'.format(mod.name))
-        if not os.path.exists(sample_directory):
-            os.makedirs(sample_directory)
-        backend = em.HDFBackend(sample_file)
-        try:
-            coords_init = backend.current_coords
-        except (AttributeError, KeyError):
-            coords_init = mod.sample_from_prior(nwalkers, seed=seed)
-    else:
-        backend = em.Backend()
-        coords_init = mod.sample_from_prior(nwalkers, seed=seed)
-
-    if mixedmoves:
-        moves = [(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)]
-    else:
-        moves = em.KDEMove()
-
-    sampler = em.Sampler(moves, backend=backend)
+    store = _chain_store(mod, sample_directory)
+    sampler = em.Sampler([(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)] if mixedmoves else em.KDEMove(),
+                         backend=store)
     if overwrite:
         sampler.reset()
-        coords_init = mod.sample_from_prior(nwalkers, seed=seed)
+    ensemble = em.Ensemble(Emcee3Model(mod), _starting_coords(mod, store, nwalkers, overwrite, seed),
+                           pool=EnsemblePool() if pool is None else pool, random=rs)
 
-    if pool is None:
-        pool = EnsemblePool()
-
-    ensemble = em.Ensemble(walker, coords_init, pool=pool, random=rs)
-
-    def calc_stats(s):
-        tau = s.get_integrated_autocorr_time(c=1)
-        tau_max = tau.max()
-        neff = s.backend.niter / tau_max - nburn
+    tau_max, converged = 0, False
+    if not overwrite:                                   # a chain left by an earlier call may already be long enough
         if verbose:
-            print("Maximum autocorrelation time: {0}".format(tau_max))
-            print("N_eff: {0}\n".format(neff * nwalkers))
-        return tau_max, neff
-
-    done = False
-    tau_max = 0
-    if not overwrite:
+            print('Status from previous run:')
         try:
-            if verbose:
-                print('Status from previous run:')
-            tau_max, neff = calc_stats(sampler)
-            if neff > targetn:
-                done = True
+            tau_max, neff = _chain_length_in_autocorr_times(sampler, nburn, nwalkers, verbose)
+            converged = neff > targetn
         except (em.AutocorrError, KeyError, AttributeError):
             pass
 
-    chunksize = iter_chunksize
-    for iteration in range(maxiter):
-        if done:
-            break
+    blocks = 0
+    while not converged and blocks < maxiter:
+        blocks += 1
         if verbose:
-            print("Iteration {0}...".format(iteration + 1))
-        sampler.run(ensemble, chunksize, progress=verbose)
+            print("Iteration {0}...".format(blocks))
+        sampler.run(ensemble, iter_chunksize, progress=verbose)
         try:
-            tau_max, neff = calc_stats(sampler)
+            tau_max, neff = _chain_length_in_autocorr_times(sampler, nburn, nwalkers, verbose)
         except em.AutocorrError:
             tau_max = 0
             continue
-        if neff > targetn:
-            done = True
+        converged = neff > targetn
 
     burnin = int(nburn * tau_max)
-    ntot = nsamples
-    samples = sampler.get_coords(flat=True, discard=burnin)
-    total_samples = len(samples)
-    if ntot > total_samples:
-        ntot = total_samples
+    flat = sampler.get_coords(flat=True, discard=burnin)
+    keep = min(nsamples, len(flat))
     if verbose:
         print("Discarding {0} samples for burn-in".format(burnin))
-        print("Randomly choosing {0} samples".format(ntot))
-    inds = rs.choice(total_samples, size=ntot, replace=False)
-    samples = samples[inds]
-
-    df = pd.DataFrame(samples, columns=mod.param_names)
+        print("Randomly choosing {0} samples".format(keep))
+    df = pd.DataFrame(flat[rs.choice(len(flat), size=keep, replace=False)], columns=mod.param_names)
     write_samples(mod, df, resultsdir=resultsdir)
     return df

@@ -146,31 +146,27 @@ class LightCurve(object):
         self._invalidate()
 
     def best_sublc(self, ndays, npoints=600, chunksize=300, flat_order=3, **kwargs):
-        """New sub-LightCurve over the ``ndays`` window with the largest detrended rms, subsampled to about
-        ``npoints`` points (gprot/lc.py:226-265)."""
-        x_full, y_full = self.x_full, self.y_full
-        N = len(x_full)
-        cadence = np.median(x_full[1:] - x_full[:-1])
-        window = int(ndays / cadence)
-        stepsize = max(window // 50, 1)
-        i1, i2 = 0, window
-        max_std, max_i1, max_i2 = 0, None, None
-        while i2 < N:
-            x, y = x_full[i1:i2].copy(), y_full[i1:i2].copy()
-            x, y, _ = sigma_clip(x, y, y, 5)
-            p = np.polyfit(x, y, flat_order)
-            y -= np.polyval(p, x)
-            std = np.std(y)
-            if std > max_std:
-                max_i1, max_i2, max_std = i1, i2, std
-            i1 += stepsize
-            i2 += stepsize
-        if max_i1 is None:                      # window longer than the light curve: use all of it
-            max_i1, max_i2 = 0, N
-        x, y, yerr = x_full[max_i1:max_i2], y_full[max_i1:max_i2], self.yerr_full[max_i1:max_i2]
-        if 'sub' not in kwargs:
-            kwargs['sub'] = max(window // npoints, 1)
-        return LightCurve(x, y, yerr, chunksize=chunksize, name=self.name + '_{:.0f}d'.format(ndays), **kwargs)
+        """New sub-LightCurve over the ``ndays``-long window of the full-resolution data with the largest rms after
+        5-sigma clipping and removal of a polynomial of order ``flat_order``; windows advance by 1/50 of their length;
+        the result is subsampled to about ``npoints`` points (gprot/lc.py:226-265)."""
+        xf, yf, ef = self.x_full, self.y_full, self.yerr_full
+        width = int(ndays / np.median(np.diff(xf)))
+        hop = max(width // 50, 1)
+
+        def variability(lo):
+            xs, ys, _ = sigma_clip(xf[lo:lo + width].copy(), yf[lo:lo + width].copy(), yf[lo:lo + width], 5)
+            return np.std(ys - np.polyval(np.polyfit(xs, ys, flat_order), xs))
+
+        starts = range(0, max(len(xf) - width, 0), hop)        # windows that end before the last point, as the reference scans
+        scores = [variability(lo) for lo in starts]
+        if scores and max(scores) > 0:
+            lo = starts[int(np.argmax(scores))]                # first maximum wins, like a strict '>' scan
+            hi = lo + width
+        else:                                                   # window longer than the light curve: use all of it
+            lo, hi = 0, len(xf)
+        kwargs.setdefault('sub', max(width // npoints, 1))
+        return LightCurve(xf[lo:hi], yf[lo:hi], ef[lo:hi], chunksize=chunksize,
+                          name=self.name + '_{:.0f}d'.format(ndays), **kwargs)
 
     def make_best_chunks(self, ndays=(800, 200, 50), seed=None, **kwargs):
         """Chunk lists built from the most variable 800 / 200 / 50 day windows (gprot/lc.py:267-281); the
