@@ -86,6 +86,11 @@ summary = {
         "evaluations": len(chk), "gpu_closer_than_oracle": int(sum(r["gpu_vs_long_double"] <= r["oracle_vs_long_double"] for r in chk)),
         "median_gpu": float(np.median([r["gpu_vs_long_double"] for r in chk])) if chk else None,
         "median_oracle": float(np.median([r["oracle_vs_long_double"] for r in chk])) if chk else None},
+    "largest_in_units_of_eps_cond": [dict(n=r["n"], chunksize=r["chunksize"], cluster=r["cluster"], exact=r["exact"], cond=r["cond"],
+                                          ref=r["ref"], rel_err=abs(r["got"] - r["ref"]) / abs(r["ref"]),
+                                          units=abs(r["got"] - r["ref"]) / abs(r["ref"]) / (1.1e-16 * r["cond"]),
+                                          gpu_vs_long_double=r.get("gpu_vs_long_double"), oracle_vs_long_double=r.get("oracle_vs_long_double"))
+                                     for r in sorted(fin, key=lambda r: -abs(r["got"] - r["ref"]) / abs(r["ref"]) / r["cond"])[:6]],
     "worst": [dict(n=r["n"], chunksize=r["chunksize"], cluster=r["cluster"], exact=r["exact"], cond=r["cond"], ref=r["ref"],
                    rel_err=abs(r["got"] - r["ref"]) / abs(r["ref"]), gpu_vs_long_double=r.get("gpu_vs_long_double"),
                    oracle_vs_long_double=r.get("oracle_vs_long_double")) for r in worst],
