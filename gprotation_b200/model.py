@@ -279,6 +279,45 @@ class GPRotModel(object):
         post[~np.isfinite(lp)] = -np.inf
         return post
 
+    # ---- predictive distribution (what the reference's plotting scripts get from george's gp.predict, code/koi_demo.py:66)
+    def predict(self, theta, t_pred, return_var=True, device=None):
+        """GP predictive mean (and variance) at ``t_pred`` for hyper-parameters ``theta``, computed with the batched
+        likelihood itself: the log-likelihood of the data extended by one point (t*, y*) is exactly quadratic in y*,
+        ``lnL(y*) = const - (y* - mu*)^2 / (2 s*^2)``, so three evaluations at y* = -s, 0, +s give mu* and s*^2.  Every test
+        point is three (N+1)-point problems; all of them go to the device in ONE launch.  The variance returned is
+        george's: k(t*, t*) minus the explained part, i.e. without the measurement noise of a new observation.  With a
+        chunked light curve the prediction uses the chunk whose time span is nearest to t* (chunks are independent in
+        the reference's likelihood)."""
+        theta = np.asarray(theta, dtype=np.float64).reshape(5)
+        t_pred = np.atleast_1d(np.asarray(t_pred, dtype=np.float64))
+        A, L, G, S, P = np.exp(theta)
+        s = float(np.sqrt(A + S))
+        lc = self.lc
+        if lc.x_list is None:
+            groups = [(np.asarray(lc.x), np.asarray(lc.y), np.asarray(lc.yerr))]
+        else:
+            groups = [(np.asarray(a), np.asarray(b), np.asarray(c)) for a, b, c in zip(lc.x_list, lc.y_list, lc.yerr_list)]
+        eng = _engine.GPEngine(self._device if device is None else device)      # scratch context: the model's own stays untouched
+        try:
+            ids = []
+            for ts in t_pred:
+                gap = [max(g[0].min() - ts, ts - g[0].max(), 0.0) for g in groups]
+                x, y, e = groups[int(np.argmin(gap))]
+                xa, ea = np.append(x, ts), np.append(e, 0.0)
+                for ystar in (-s, 0.0, s):
+                    ids.append(eng.register_lc(xa, np.append(y, ystar), ea))
+            f = eng.lnlike_batch(np.tile(theta, (len(ids), 1)), lc_id=np.asarray(ids, dtype=np.int32)).reshape(-1, 3)
+        finally:
+            eng.close()
+        curv = (f[:, 2] + f[:, 0] - 2.0 * f[:, 1]) / (s * s)        # = -1 / s*^2
+        slope = (f[:, 2] - f[:, 0]) / (2.0 * s)                     # = mu* / s*^2
+        with np.errstate(divide='ignore', invalid='ignore'):
+            var_obs = -1.0 / curv
+            mu = slope * var_obs
+        if not return_var:
+            return mu
+        return mu, var_obs - S                                       # the extended point carried S + 0^2 of extra noise
+
     # ---- nested-sampling shims (gprot/model.py:371-388)
     def polychord_prior(self, cube):
         return [lo + (hi - lo) * cube[i] for i, (lo, hi) in enumerate(self.bounds)]

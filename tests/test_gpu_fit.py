@@ -73,3 +73,26 @@ def test_gprot_fit_cli_on_aigrain_layout(engine, tmp_path, monkeypatch):
     assert os.path.exists(str(tmp_path / "mcmc_chains" / "0.npz"))
     # a star that does not exist is logged and skipped, not raised (scripts/gprot-fit:210-213)
     assert cli.main("9 --aigrain --nwalkers 20 --maxiter 1".split()) == 1
+
+
+def test_predict_through_the_likelihood(engine):
+    """GPRotModel.predict (three batched likelihoods per test point) against the dense textbook formulas with the
+    matrix the reference's code builds: mu* = k*^T K^-1 y, var* = k(t*,t*) - k*^T K^-1 k*."""
+    t, y, yerr, truth = synthetic_lightcurve(31, 260, baseline=120.0, kind="gp")
+    mod = GPRotModel(LightCurve(t, y, yerr, name="p", chunksize=None), engine=engine)
+    tp = np.array([t[0] - 3.0, 0.5 * (t[100] + t[101]), t[57], t[-1] + 1.5, 60.123])
+    mu, var = mod.predict(truth, tp)
+    A, L, G, S, P = np.exp(truth)
+    K = o.kernel_matrix(truth, t, yerr)
+
+    def k(a, b):
+        d = a[:, None] - b[None, :]
+        out = A * np.exp(-0.5 * d * d / L) * np.exp(-G * np.sin(np.pi * d / P) ** 2)
+        return out + S * (d * d / L < np.finfo(float).eps)            # WhiteKernel at coincident inputs
+    ks = k(tp, t)
+    ref_mu = ks @ np.linalg.solve(K, y)
+    ref_var = (A + S) - np.einsum('ij,ji->i', ks, np.linalg.solve(K, ks.T))
+    scale = np.sqrt(A + S)
+    assert np.all(np.abs(mu - ref_mu) <= 1e-6 * scale)
+    assert np.all(np.abs(var - ref_var) <= 1e-6 * (A + S))
+    assert var[2] < 0.1 * (A + S) and var[0] > var[1]                 # on a data point: small; outside the data: larger
