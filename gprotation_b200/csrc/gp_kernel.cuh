@@ -24,9 +24,6 @@
 #include <math.h>
 #include <float.h>
 
-#ifndef PIVOT_VARIANT
-#define PIVOT_VARIANT 1   // 1: all-lane pivot tile (tile8_factor_all), 0: lane-distributed (tile8_factor); tools/tile8_bench.cu compares them
-#endif
 namespace gprot {
 
 constexpr int BS = 128;           // block edge
@@ -157,6 +154,15 @@ __device__ __forceinline__ int w_off(int c, int m) {
     const int s = m >> 4;
     return w_slab_off(s) + ((c >> 3) - 2 * s) * 128 + ((m >> 3) & 1) * 64 + (((c & 7) << 2) + (m & 3)) * 2 + ((m >> 2) & 1);
 }
+
+// Geometry of the diagonal-block sweep, shared by the two kernels (gp_kernel64.cuh has its own for 64 x 64 blocks)
+struct Geo128 {
+    static constexpr int LD = 132;        // LDM: pitch of the diagonal workspace
+    static constexpr int NR = 16;         // 8 x 8 tile rows of a diagonal block
+    static constexpr int NTH = 512;       // threads of the CTA
+    __device__ static __forceinline__ int wslab(int s) { return w_slab_off(s); }
+    __device__ static __forceinline__ int woff(int c, int m) { return w_off(c, m); }
+};
 
 // Store a warp's 32 x 32 C-fragment tile (acc[mi][ni][e] at row 8mi+g, col 8ni+2q+e) into a fragment-major
 // block at tile origin (row0, col0), optionally negated.  Lanes q and q^2 hold neighbouring doubles of the
@@ -445,14 +451,15 @@ __device__ __forceinline__ void tile8_factor(Smem& sm, int p, int buf, int lane)
 // same elimination (the dependent chain is rsqrt -> scale -> one DFMA per pivot); lane b < 8 then forms column b of
 // the inverse by forward substitution.  Needs ~100 registers, which only the pivot warp's own loop can afford.
 // Same outputs as tile8_factor<true>: W_pp (sm.wt[buf] and its place in sm.W), 1/diag (sm.dinv).
-__device__ __forceinline__ void tile8_factor_all(Smem& sm, int p, int buf, int lane) {
-    const double* Mp = sm.regionA + (8 * p) * LDM + 8 * p;
+template <class G, class SM>
+__device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lane) {
+    const double* Mp = sm.regionA + (8 * p) * G::LD + 8 * p;
     double l[8][8];
 #pragma unroll
     for (int a = 0; a < 8; a++) {
 #pragma unroll
         for (int b2 = 0; b2 <= a / 2; b2++) {
-            const double2 v = *reinterpret_cast<const double2*>(Mp + a * LDM + 2 * b2);
+            const double2 v = *reinterpret_cast<const double2*>(Mp + a * G::LD + 2 * b2);
             l[a][2 * b2] = v.x;
             if (2 * b2 + 1 <= a) l[a][2 * b2 + 1] = v.y;
         }
@@ -487,7 +494,7 @@ __device__ __forceinline__ void tile8_factor_all(Smem& sm, int p, int buf, int l
 #pragma unroll
         for (int a = 0; a < 8; a++) {
             wt[a * 8 + b] = w[a];
-            sm.W[w_off(8 * p + a, 8 * p + b)] = w[a];
+            sm.W[G::woff(8 * p + a, 8 * p + b)] = w[a];
         }
         sm.dinv[8 * p + b] = w[b];
     }
@@ -505,13 +512,13 @@ __device__ __forceinline__ void tile8_factor_all(Smem& sm, int p, int buf, int l
 // Finished tiles of W = L_JJ^{-1} go straight to their B-operand position in sm.W (no conversion pass).
 // rank-8 update of the register tiles C = P+2 .. chi of one tile row with panel column P (a0, a1 = A fragment of -X(R));
 // the tile that becomes the next-but-one panel column (C = P+2) is parked in shared memory right after its update
-template <int P>
-__device__ __forceinline__ void rows_update(double (&rt)[16][2], const double* __restrict__ bcol, double* myrow, double a0,
+template <class G, int P>
+__device__ __forceinline__ void rows_update(double (&rt)[G::NR][2], const double* __restrict__ bcol, double* myrow, double a0,
                                             double a1, int chi, int q) {
 #pragma unroll
-    for (int C = P + 2; C < 16; C++) {
+    for (int C = P + 2; C < G::NR; C++) {
         if (C <= chi) {
-            const double b0 = bcol[(8 * C) * LDM + q], b1 = bcol[(8 * C) * LDM + q + 4];
+            const double b0 = bcol[(8 * C) * G::LD + q], b1 = bcol[(8 * C) * G::LD + q + 4];
             dmma(rt[C][0], rt[C][1], a0, b0);
             dmma(rt[C][0], rt[C][1], a1, b1);
             if (C == P + 2) *reinterpret_cast<double2*>(myrow + 8 * C + 2 * q) = make_double2(rt[C][0], rt[C][1]);
@@ -530,7 +537,8 @@ __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("
 
 // X = M(R, p) W_pp^T for one tile row, rewritten in place; rows above the pivot (R < p) also deliver the finished
 // tile of W^T to sm.W.  Returns the A fragment of -X.
-__device__ __forceinline__ void panel_scale(Smem& sm, double* row, const double* wt, int R, int p, int g, int q, double& a0, double& a1) {
+template <class G, class SM>
+__device__ __forceinline__ void panel_scale(SM& sm, double* row, const double* wt, int R, int p, int g, int q, double& a0, double& a1) {
     const double x0 = row[q], x1 = row[q + 4];
     const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
     double c0 = 0.0, c1 = 0.0;
@@ -539,8 +547,8 @@ __device__ __forceinline__ void panel_scale(Smem& sm, double* row, const double*
     __syncwarp();
     *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
     if (R < p) {                                               // W[8p + 2q + e][8R + g]
-        sm.W[w_off(8 * p + 2 * q, 8 * R + g)] = c0;
-        sm.W[w_off(8 * p + 2 * q + 1, 8 * R + g)] = c1;
+        sm.W[G::woff(8 * p + 2 * q, 8 * R + g)] = c0;
+        sm.W[G::woff(8 * p + 2 * q + 1, 8 * R + g)] = c1;
     }
     __syncwarp();
     a0 = -row[q]; a1 = -row[q + 4];
@@ -552,21 +560,19 @@ __device__ __forceinline__ void panel_scale(Smem& sm, double* row, const double*
 // hands the finished pivot tile to warp 0 through named barrier 1 (then updates row 0 while warp 0 factors).
 // nsteps < 16: rows 8 nsteps .. 127 of the block are identity padding; the sweep stops early and diag_pad_identity
 // fills their part of W.  Ends with a block barrier.
-__device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, int nsteps) {
+template <class G, class SM>
+__device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int nsteps) {
+    constexpr int LD = G::LD, NR = G::NR;
     const int g = lane >> 2, q = lane & 3;
     double* M = sm.regionA;
     if (warp == 0) {
-#if PIVOT_VARIANT == 1
-        tile8_factor_all(sm, 0, 0, lane);
-#else
-        tile8_factor<true>(sm, 0, 0, lane);
-#endif
+        tile8_factor_all<G>(sm, 0, 0, lane);
         __syncthreads();
         for (int p = 0; p < nsteps; p++) {
             TS(p, 0);
             if (p >= 1) {
                 double a0, a1;
-                panel_scale(sm, M + g * LDM + 8 * p, sm.wt + 64 * (p & 1), 0, p, g, q, a0, a1);
+                panel_scale<G>(sm, M + g * LD + 8 * p, sm.wt + 64 * (p & 1), 0, p, g, q, a0, a1);
             }
             TS(p, 1);
             __syncthreads();
@@ -574,21 +580,17 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
             if (p == nsteps - 1) break;
             named_sync(1, 64);                                 // pivot tile (p+1, p+1) is final
             TS(p, 3);
-#if PIVOT_VARIANT == 1
-            tile8_factor_all(sm, p + 1, (p + 1) & 1, lane);
-#else
-            tile8_factor<true>(sm, p + 1, (p + 1) & 1, lane);
-#endif
+            tile8_factor_all<G>(sm, p + 1, (p + 1) & 1, lane);
             TS(p, 4);
             __syncthreads();
         }
         return;
     }
     const int R = warp;
-    double* myrow = M + (8 * R + g) * LDM;
-    double rt[16][2];                                          // rt[C] = C fragment of tile (R, C), C >= 2
+    double* myrow = M + (8 * R + g) * LD;
+    double rt[NR][2];                                          // rt[C] = C fragment of tile (R, C), C >= 2
 #pragma unroll
-    for (int C = 2; C < 16; C++) {
+    for (int C = 2; C < NR; C++) {
         if (C <= R) {
             const double2 v = *reinterpret_cast<const double2*>(myrow + 8 * C + 2 * q);
             rt[C][0] = v.x; rt[C][1] = v.y;
@@ -599,16 +601,16 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
         const int P0 = 8 * p;
         const double* wt = sm.wt + 64 * (p & 1);
         double a0, a1;                                         // A fragment of -X(R)
-        if (R != p) panel_scale(sm, myrow + P0, wt, R, p, g, q, a0, a1);
+        if (R != p) panel_scale<G>(sm, myrow + P0, wt, R, p, g, q, a0, a1);
         else { a0 = -wt[q * 8 + g]; a1 = -wt[(q + 4) * 8 + g]; }     // rows of the pivot tile act through W_pp^T
         __syncthreads();                                       // X(C), C > p, visible to every warp
         if (p == nsteps - 1) break;
-        const int chi = (R <= p) ? 15 : R;                     // tiles p+1 .. chi of this row take the rank-8 update
-        const double* bcol = M + g * LDM + P0;                 // B fragments: X(C) at bcol + 8 C LDM
+        const int chi = (R <= p) ? NR - 1 : R;                     // tiles p+1 .. chi of this row take the rank-8 update
+        const double* bcol = M + g * LD + P0;                 // B fragments: X(C) at bcol + 8 C LDM
         {                                                      // the next panel column lives in shared memory
             double2* cp = reinterpret_cast<double2*>(myrow + P0 + 8 + 2 * q);
             double2 c = *cp;
-            const double b0 = bcol[8 * (p + 1) * LDM + q], b1 = bcol[8 * (p + 1) * LDM + q + 4];
+            const double b0 = bcol[8 * (p + 1) * LD + q], b1 = bcol[8 * (p + 1) * LD + q + 4];
             dmma(c.x, c.y, a0, b0);
             dmma(c.x, c.y, a1, b1);
             *cp = c;
@@ -620,12 +622,12 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
             // tile row 0 (kept in shared memory): tiles (0, C), C = p+1 .. 15
             double r0, r1;
             if (p == 0) { r0 = -wt[q * 8 + g]; r1 = -wt[(q + 4) * 8 + g]; }
-            else { r0 = -M[g * LDM + P0 + q]; r1 = -M[g * LDM + P0 + q + 4]; }
-            const double* bp = bcol + 8 * (p + 1) * LDM + q;
-            double* cp = M + g * LDM + P0 + 8 + 2 * q;
+            else { r0 = -M[g * LD + P0 + q]; r1 = -M[g * LD + P0 + q + 4]; }
+            const double* bp = bcol + 8 * (p + 1) * LD + q;
+            double* cp = M + g * LD + P0 + 8 + 2 * q;
             int C = p + 1;
-            for (; C + 1 <= 15; C += 2, bp += 16 * LDM, cp += 16) {
-                const double b00 = bp[0], b01 = bp[4], b10 = bp[8 * LDM], b11 = bp[8 * LDM + 4];
+            for (; C + 1 <= NR - 1; C += 2, bp += 16 * LD, cp += 16) {
+                const double b00 = bp[0], b01 = bp[4], b10 = bp[8 * LD], b11 = bp[8 * LD + 4];
                 double2 x = *reinterpret_cast<double2*>(cp), y = *reinterpret_cast<double2*>(cp + 8);
                 dmma(x.x, x.y, r0, b00);
                 dmma(y.x, y.y, r0, b10);
@@ -634,7 +636,7 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
                 *reinterpret_cast<double2*>(cp) = x;
                 *reinterpret_cast<double2*>(cp + 8) = y;
             }
-            if (C <= 15) {
+            if (C <= NR - 1) {
                 const double b00 = bp[0], b01 = bp[4];
                 double2 x = *reinterpret_cast<double2*>(cp);
                 dmma(x.x, x.y, r0, b00);
@@ -643,20 +645,20 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
             }
         } else {
             switch (p) {
-                case 0: rows_update<0>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 1: rows_update<1>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 2: rows_update<2>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 3: rows_update<3>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 4: rows_update<4>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 5: rows_update<5>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 6: rows_update<6>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 7: rows_update<7>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 8: rows_update<8>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 9: rows_update<9>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 10: rows_update<10>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 11: rows_update<11>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 12: rows_update<12>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 13: rows_update<13>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 0: if constexpr (0 <= NR - 3) rows_update<G, 0>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 1: if constexpr (1 <= NR - 3) rows_update<G, 1>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 2: if constexpr (2 <= NR - 3) rows_update<G, 2>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 3: if constexpr (3 <= NR - 3) rows_update<G, 3>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 4: if constexpr (4 <= NR - 3) rows_update<G, 4>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 5: if constexpr (5 <= NR - 3) rows_update<G, 5>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 6: if constexpr (6 <= NR - 3) rows_update<G, 6>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 7: if constexpr (7 <= NR - 3) rows_update<G, 7>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 8: if constexpr (8 <= NR - 3) rows_update<G, 8>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 9: if constexpr (9 <= NR - 3) rows_update<G, 9>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 10: if constexpr (10 <= NR - 3) rows_update<G, 10>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 11: if constexpr (11 <= NR - 3) rows_update<G, 11>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 12: if constexpr (12 <= NR - 3) rows_update<G, 12>(rt, bcol, myrow, a0, a1, chi, q); break;
+                case 13: if constexpr (13 <= NR - 3) rows_update<G, 13>(rt, bcol, myrow, a0, a1, chi, q); break;
                 default: break;
             }
         }
@@ -665,27 +667,29 @@ __device__ __forceinline__ void diag_factor_rows(Smem& sm, int warp, int lane, i
 }
 
 // rows c >= c0 of W (and of 1/diag) are those of the identity
-__device__ __forceinline__ void diag_pad_identity(Smem& sm, int c0, int tid) {
-    for (int s = 0; s < 8; s++) {
-        const int cnt = (16 - 2 * s) * 128;
-        double* dst = sm.W + w_slab_off(s);
-        for (int d = tid; d < cnt; d += NT) {
+template <class G, class SM>
+__device__ __forceinline__ void diag_pad_identity(SM& sm, int c0, int tid) {
+    for (int s = 0; s < G::NR / 2; s++) {
+        const int cnt = (G::NR - 2 * s) * 128;
+        double* dst = sm.W + G::wslab(s);
+        for (int d = tid; d < cnt; d += G::NTH) {
             const int rgrel = d >> 7, kp = (d >> 6) & 1, ln = (d >> 1) & 31, hh = d & 1;
             const int c = 8 * (2 * s + rgrel) + (ln >> 2);
             const int m = 16 * s + 4 * (2 * kp + hh) + (ln & 3);
             if (c >= c0) dst[d] = (m == c) ? 1.0 : 0.0;
         }
     }
-    if (tid >= c0 && tid < BS) sm.dinv[tid] = 1.0;
+    if (tid >= c0 && tid < 8 * G::NR) sm.dinv[tid] = 1.0;
 }
 
 // z_J = W ytilde_J as a DMMA matrix-vector product (ytilde in column 0 of the B operand), |z_J|^2 and sum log L_rr.
 // Warp w owns rows 8w..8w+7; k runs over the slabs 0..w/2 of sm.W (zeros above the diagonal are stored).
-__device__ __forceinline__ void diag_solve(Smem& sm, int warp, int lane) {
+template <class G, class SM>
+__device__ __forceinline__ void diag_solve(SM& sm, int warp, int lane) {
     const int g = lane >> 2, q = lane & 3;
     double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0;
     for (int s = 0; s <= (warp >> 1); s++) {
-        const double* base = sm.W + w_slab_off(s) + (warp - 2 * s) * 128 + lane * 2;
+        const double* base = sm.W + G::wslab(s) + (warp - 2 * s) * 128 + lane * 2;
         const double2 f0 = *reinterpret_cast<const double2*>(base);
         const double2 f1 = *reinterpret_cast<const double2*>(base + 64);
         const double* yk = sm.yj + 16 * s + q;
@@ -852,16 +856,16 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 {
                     const int nreal = min(BS, n - J * BS);          // the rest of the block is identity padding
                     const int nsteps = (nreal + 7) >> 3;
-                    diag_factor_rows(sm, warp, lane, nsteps);       // ends with __syncthreads
+                    diag_factor_rows<Geo128>(sm, warp, lane, nsteps);       // ends with __syncthreads
                     if (nsteps < 16) {
-                        diag_pad_identity(sm, 8 * nsteps, tid);
+                        diag_pad_identity<Geo128>(sm, 8 * nsteps, tid);
                         __syncthreads();
                     }
                 }
                 TICK(4);
             }
             if (sm.fail) return false;
-            diag_solve(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
+            diag_solve<Geo128>(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
             if (nextI >= 0) stage_points(sm.rowv, vt, prm.npad_max, nextI, tid);   // row side of the first block below
             fence_async();
             __syncthreads();

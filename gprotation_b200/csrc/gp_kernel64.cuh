@@ -125,208 +125,15 @@ __device__ __forceinline__ void accumulate2(Smem2& sm, double (&acc)[4][4][2], u
     }
 }
 
-// ---------------------------------------------------------------- diagonal block (64 x 64): the sweep of gp_kernel.cuh with 8 tile rows
-__device__ __forceinline__ void tile8_factor_all2(Smem2& sm, int p, int buf, int lane) {
-    const double* Mp = sm.regionA + (8 * p) * LDM2 + 8 * p;
-    double l[8][8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) {
-#pragma unroll
-        for (int b2 = 0; b2 <= a / 2; b2++) {
-            const double2 v = *reinterpret_cast<const double2*>(Mp + a * LDM2 + 2 * b2);
-            l[a][2 * b2] = v.x;
-            if (2 * b2 + 1 <= a) l[a][2 * b2 + 1] = v.y;
-        }
-    }
-    double rinv[8];
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const double d = l[j][j];
-        if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
-        const double ri = rsqrt_pos(d);
-        rinv[j] = ri;
-#pragma unroll
-        for (int a = j + 1; a < 8; a++) l[a][j] *= ri;
-#pragma unroll
-        for (int a = j + 1; a < 8; a++)
-#pragma unroll
-            for (int b = j + 1; b <= a; b++) l[a][b] = fma(-l[a][j], l[b][j], l[a][b]);
-    }
-    const int b = lane & 7;
-    double w[8];
-#pragma unroll
-    for (int a = 0; a < 8; a++) {
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < a; m++) s = fma(l[a][m], w[m], s);
-        w[a] = (a == b) ? rinv[a] : ((a > b) ? -rinv[a] * s : 0.0);
-    }
-    if (lane < 8) {
-        double* wt = sm.wt + 64 * buf;
-#pragma unroll
-        for (int a = 0; a < 8; a++) {
-            wt[a * 8 + b] = w[a];
-            sm.W[w2_off(8 * p + a, 8 * p + b)] = w[a];
-        }
-        sm.dinv[8 * p + b] = w[b];
-    }
-    if (bad && lane == 0) sm.fail = 1;
-}
-
-template <int P>
-__device__ __forceinline__ void rows_update2(double (&rt)[8][2], const double* __restrict__ bcol, double* myrow, double a0, double a1,
-                                             int chi, int q) {
-#pragma unroll
-    for (int C = P + 2; C < 8; C++) {
-        if (C <= chi) {
-            const double b0 = bcol[(8 * C) * LDM2 + q], b1 = bcol[(8 * C) * LDM2 + q + 4];
-            dmma(rt[C][0], rt[C][1], a0, b0);
-            dmma(rt[C][0], rt[C][1], a1, b1);
-            if (C == P + 2) *reinterpret_cast<double2*>(myrow + 8 * C + 2 * q) = make_double2(rt[C][0], rt[C][1]);
-        }
-    }
-}
-
-__device__ __forceinline__ void panel_scale2(Smem2& sm, double* row, const double* wt, int R, int p, int g, int q, double& a0, double& a1) {
-    const double x0 = row[q], x1 = row[q + 4];
-    const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
-    double c0 = 0.0, c1 = 0.0;
-    dmma(c0, c1, x0, b0);
-    dmma(c0, c1, x1, b1);
-    __syncwarp();
-    *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
-    if (R < p) {
-        sm.W[w2_off(8 * p + 2 * q, 8 * R + g)] = c0;
-        sm.W[w2_off(8 * p + 2 * q + 1, 8 * R + g)] = c1;
-    }
-    __syncwarp();
-    a0 = -row[q]; a1 = -row[q + 4];
-}
-
-// warp 0: pivot warp (and tile row 0's scaling); warps 1..7 own tile rows 1..7; ends with a block barrier
-__device__ __forceinline__ void diag_factor_rows2(Smem2& sm, int warp, int lane, int nsteps) {
-    const int g = lane >> 2, q = lane & 3;
-    double* M = sm.regionA;
-    if (warp == 0) {
-        tile8_factor_all2(sm, 0, 0, lane);
-        __syncthreads();
-        for (int p = 0; p < nsteps; p++) {
-            if (p >= 1) {
-                double a0, a1;
-                panel_scale2(sm, M + g * LDM2 + 8 * p, sm.wt + 64 * (p & 1), 0, p, g, q, a0, a1);
-            }
-            __syncthreads();
-            if (p == nsteps - 1) break;
-            named_sync(1, 64);
-            tile8_factor_all2(sm, p + 1, (p + 1) & 1, lane);
-            __syncthreads();
-        }
-        return;
-    }
-    const int R = warp;
-    double* myrow = M + (8 * R + g) * LDM2;
-    double rt[8][2];
-#pragma unroll
-    for (int C = 2; C < 8; C++) {
-        if (C <= R) {
-            const double2 v = *reinterpret_cast<const double2*>(myrow + 8 * C + 2 * q);
-            rt[C][0] = v.x; rt[C][1] = v.y;
-        } else { rt[C][0] = 0.0; rt[C][1] = 0.0; }
-    }
-    __syncthreads();
-    for (int p = 0; p < nsteps; p++) {
-        const int P0 = 8 * p;
-        const double* wt = sm.wt + 64 * (p & 1);
-        double a0, a1;
-        if (R != p) panel_scale2(sm, myrow + P0, wt, R, p, g, q, a0, a1);
-        else { a0 = -wt[q * 8 + g]; a1 = -wt[(q + 4) * 8 + g]; }
-        __syncthreads();
-        if (p == nsteps - 1) break;
-        const int chi = (R <= p) ? 7 : R;
-        const double* bcol = M + g * LDM2 + P0;
-        {
-            double2* cp = reinterpret_cast<double2*>(myrow + P0 + 8 + 2 * q);
-            double2 c = *cp;
-            const double b0 = bcol[8 * (p + 1) * LDM2 + q], b1 = bcol[8 * (p + 1) * LDM2 + q + 4];
-            dmma(c.x, c.y, a0, b0);
-            dmma(c.x, c.y, a1, b1);
-            *cp = c;
-        }
-        if (R == p + 1) {
-            __syncwarp();
-            __threadfence_block();
-            named_arrive(1, 64);
-            double r0, r1;
-            if (p == 0) { r0 = -wt[q * 8 + g]; r1 = -wt[(q + 4) * 8 + g]; }
-            else { r0 = -M[g * LDM2 + P0 + q]; r1 = -M[g * LDM2 + P0 + q + 4]; }
-            const double* bp = bcol + 8 * (p + 1) * LDM2 + q;
-            double* cp = M + g * LDM2 + P0 + 8 + 2 * q;
-            for (int C = p + 1; C <= 7; C++, bp += 8 * LDM2, cp += 8) {
-                const double b00 = bp[0], b01 = bp[4];
-                double2 x = *reinterpret_cast<double2*>(cp);
-                dmma(x.x, x.y, r0, b00);
-                dmma(x.x, x.y, r1, b01);
-                *reinterpret_cast<double2*>(cp) = x;
-            }
-        } else {
-            switch (p) {
-                case 0: rows_update2<0>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 1: rows_update2<1>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 2: rows_update2<2>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 3: rows_update2<3>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 4: rows_update2<4>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 5: rows_update2<5>(rt, bcol, myrow, a0, a1, chi, q); break;
-                default: break;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-__device__ __forceinline__ void diag_pad_identity2(Smem2& sm, int c0, int tid) {
-    for (int s = 0; s < 4; s++) {
-        const int cnt = (8 - 2 * s) * 128;
-        double* dst = sm.W + w2_slab_off(s);
-        for (int d = tid; d < cnt; d += NT2) {
-            const int rgrel = d >> 7, kp = (d >> 6) & 1, ln = (d >> 1) & 31, hh = d & 1;
-            const int c = 8 * (2 * s + rgrel) + (ln >> 2);
-            const int m = 16 * s + 4 * (2 * kp + hh) + (ln & 3);
-            if (c >= c0) dst[d] = (m == c) ? 1.0 : 0.0;
-        }
-    }
-    if (tid >= c0 && tid < BC) sm.dinv[tid] = 1.0;
-}
-
-// z_J = W ytilde_J (DMMA matrix-vector product), |z_J|^2, sum log L_rr; warp w owns rows 8w .. 8w+7
-__device__ __forceinline__ void diag_solve2(Smem2& sm, int warp, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-    double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0;
-    for (int s = 0; s <= (warp >> 1); s++) {
-        const double* base = sm.W + w2_slab_off(s) + (warp - 2 * s) * 128 + lane * 2;
-        const double2 f0 = *reinterpret_cast<const double2*>(base);
-        const double2 f1 = *reinterpret_cast<const double2*>(base + 64);
-        const double* yk = sm.yj + 16 * s + q;
-        const double y0 = g == 0 ? yk[0] : 0.0, y1 = g == 0 ? yk[4] : 0.0, y2 = g == 0 ? yk[8] : 0.0, y3 = g == 0 ? yk[12] : 0.0;
-        dmma(za0, za1, f0.x, y0);
-        dmma(zb0, zb1, f0.y, y1);
-        dmma(za0, za1, f1.x, y2);
-        dmma(zb0, zb1, f1.y, y3);
-    }
-    const double z = za0 + zb0;
-    double z2 = 0.0, lg = 0.0;
-    if (q == 0) {
-        sm.zs[8 * warp + g] = z;
-        z2 = z * z;
-        lg = -log(sm.dinv[8 * warp + g]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        z2 += __shfl_xor_sync(0xffffffffu, z2, o);
-        lg += __shfl_xor_sync(0xffffffffu, lg, o);
-    }
-    if (lane == 0) { sm.qpart[warp] = z2; sm.lpart[warp] = lg; }
-}
+// ---------------------------------------------------------------- diagonal block (64 x 64)
+// the warp-specialised sweep of gp_kernel.cuh (diag_factor_rows / diag_pad_identity / diag_solve) with 8 tile rows
+struct Geo64 {
+    static constexpr int LD = LDM2;
+    static constexpr int NR = 8;
+    static constexpr int NTH = NT2;
+    __device__ static __forceinline__ int wslab(int s) { return w2_slab_off(s); }
+    __device__ static __forceinline__ int woff(int c, int m) { return w2_off(c, m); }
+};
 
 // ---------------------------------------------------------------- the kernel
 template <bool EXACT>
@@ -446,13 +253,13 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                 if (tid < BC) sm.yj[tid] = yw[J * BC + tid];
                 __syncthreads();
                 const int nsteps = (nreal + 7) >> 3;
-                diag_factor_rows2(sm, warp, lane, nsteps);
+                diag_factor_rows<Geo64>(sm, warp, lane, nsteps);
                 if (nsteps < 8) {
-                    diag_pad_identity2(sm, 8 * nsteps, tid);
+                    diag_pad_identity<Geo64>(sm, 8 * nsteps, tid);
                     __syncthreads();
                 }
                 if (sm.fail) { failed = true; break; }
-                diag_solve2(sm, warp, lane);
+                diag_solve<Geo64>(sm, warp, lane);
                 if (J + 1 < T) stage_points2(sm.rowv, SR, vt, prm.npad_max, (J + 1) * BC, SR, tid);
                 fence_async();
                 __syncthreads();

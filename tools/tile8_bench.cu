@@ -340,8 +340,8 @@ __global__ void __launch_bounds__(512, 1) k_diag3(long long* out, double* dump, 
             }
             __syncthreads();
         } else {
-            diag_factor_rows(sm, warp, lane, 16);
-            diag_solve(sm, warp, lane);
+            diag_factor_rows<Geo128>(sm, warp, lane, 16);
+            diag_solve<Geo128>(sm, warp, lane);
             __syncthreads();
         }
         long long t1 = clock64();
