@@ -714,6 +714,82 @@ __device__ __forceinline__ void diag_solve(SM& sm, int warp, int lane) {
     if (lane == 0) { sm.qpart[warp] = z2; sm.lpart[warp] = lg; }
 }
 
+// ---------------------------------------------------------------- TRSM as a GEMM with the inverse
+// acc <- S W^T for this warp's 32 x 32 tile: S = the staging block (A-operand slabs of 128 rows, written by
+// store_tile_frag), W = L_JJ^{-1} in B-operand layout (packed lower triangle, slab offsets from G).  k runs over
+// m <= c only; inside the two slabs that cross the diagonal the zero 8 x 4 sub-blocks of W are skipped.
+template <class G>
+__device__ __forceinline__ void trsm_tile(double (&acc)[4][4][2], const double* __restrict__ stag, const double* __restrict__ Wm,
+                                          int wr, int wc, int lane) {
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
+    for (int s = 0; s < 2 * wc; s++) {
+        const double* As = stag + s * SLAB;
+        const double* Bs = Wm + G::wslab(s) - (2 * s) * 128;
+#pragma unroll
+        for (int kp = 0; kp < 2; kp++) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+        }
+    }
+#pragma unroll
+    for (int ds = 0; ds < 2; ds++) {                   // the two slabs that cross the diagonal of W
+        const int s = 2 * wc + ds;
+        const double* As = stag + s * SLAB;
+        const double* Bs = Wm + G::wslab(s) - (2 * s) * 128;
+#pragma unroll
+        for (int kp = 0; kp < 2; kp++) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+                if (4 * ds + 2 * kp <= 2 * ni + 1) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+                    if (4 * ds + 2 * kp + hh <= 2 * ni + 1) {
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+                            dmma(acc[mi][ni][0], acc[mi][ni][1], hh ? a[mi].y : a[mi].x, hh ? b[ni].y : b[ni].x);
+                    }
+        }
+    }
+}
+
+// sum over this warp's 32 columns of L_IJ z_J for its 32 rows -> red[wc * stride + row]
+__device__ __forceinline__ void lz_partials(const double (&acc)[4][4][2], const double* __restrict__ zs, double* red, int stride,
+                                            int wr, int wc, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) {
+        const double z0 = zs[32 * wc + 8 * ni + 2 * q], z1 = zs[32 * wc + 8 * ni + 2 * q + 1];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) part[mi] = fma(acc[mi][ni][0], z0, fma(acc[mi][ni][1], z1, part[mi]));
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 1);
+        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 2);
+        if (q == 0) red[wc * stride + 32 * wr + 8 * mi + g] = part[mi];
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
 // CL = CTAs per problem.  CL > 1 launches thread-block clusters of CL CTAs that share one problem: every CTA forms the
 // diagonal block of a column (redundantly: same operands, same order, bitwise the same W and z_J -- the CTAs would
@@ -901,74 +977,11 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 __syncthreads();
                 TICK(8);
                 if (rowact) {
-                // ---- L_IJ = S W^T : k runs over m <= c
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-                for (int s = 0; s < 2 * wc; s++) {
-                    const double* As = sm.regionA + s * SLAB;
-                    const double* Bs = sm.W + w_slab_off(s) - (2 * s) * 128;
-#pragma unroll
-                    for (int kp = 0; kp < 2; kp++) {
-                        double2 a[4], b[4];
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                        for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                            for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                            for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
-                    }
-                }
-#pragma unroll
-                for (int ds = 0; ds < 2; ds++) {                   // the two slabs that cross the diagonal of W
-                    const int s = 2 * wc + ds;
-                    const double* As = sm.regionA + s * SLAB;
-                    const double* Bs = sm.W + w_slab_off(s) - (2 * s) * 128;
-#pragma unroll
-                    for (int kp = 0; kp < 2; kp++) {
-                        double2 a[4], b[4];
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                        for (int ni = 0; ni < 4; ni++)
-                            if (4 * ds + 2 * kp <= 2 * ni + 1) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                        for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-                            for (int ni = 0; ni < 4; ni++)
-                                if (4 * ds + 2 * kp + hh <= 2 * ni + 1) {
-#pragma unroll
-                                    for (int mi = 0; mi < 4; mi++)
-                                        dmma(acc[mi][ni][0], acc[mi][ni][1], hh ? a[mi].y : a[mi].x, hh ? b[ni].y : b[ni].x);
-                                }
-                    }
-                }
-                // ---- ytilde_I -= L_IJ z_J (partials per warp column), store L_IJ
-                {
-                    double part[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) {
-                        const double z0 = sm.zs[32 * wc + 8 * ni + 2 * q], z1 = sm.zs[32 * wc + 8 * ni + 2 * q + 1];
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++) part[mi] = fma(acc[mi][ni][0], z0, fma(acc[mi][ni][1], z1, part[mi]));
-                    }
-#pragma unroll
-                    for (int mi = 0; mi < 4; mi++) {
-                        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 1);
-                        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 2);
-                        if (q == 0) sm.red[wc * BS + 32 * wr + 8 * mi + g] = part[mi];
-                    }
-                }
-                // stored as each warp finishes: warps with a short triangular product overlap their stores with the
-                // others' DMMAs
-                store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
+                    trsm_tile<Geo128>(acc, sm.regionA, sm.W, wr, wc, lane);      // L_IJ = S W^T
+                    lz_partials(acc, sm.zs, sm.red, BS, wr, wc, lane);           // ytilde_I -= L_IJ z_J, per warp column
+                    // stored as each warp finishes: warps with a short triangular product overlap their stores with the
+                    // others' DMMAs
+                    store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
                 }
             if (nextI >= 0) stage_points(sm.rowv, vt, prm.npad_max, nextI, tid);   // row side of the next block
             fence_async();

@@ -290,69 +290,8 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                 if (rowact) store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc, 128-row A slabs
                 __syncthreads();
                 if (rowact) {
-#pragma unroll
-                    for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                        for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-                    for (int s = 0; s < 2 * wc; s++) {
-                        const double* As = sm.regionA + s * SLAB;
-                        const double* Bs = sm.W + w2_slab_off(s) - (2 * s) * 128;
-#pragma unroll
-                        for (int kp = 0; kp < 2; kp++) {
-                            double2 a[4], b[4];
-#pragma unroll
-                            for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                            for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
-#pragma unroll
-                            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
-                        }
-                    }
-#pragma unroll
-                    for (int ds = 0; ds < 2; ds++) {               // the two slabs that cross the diagonal of W
-                        const int s = 2 * wc + ds;
-                        const double* As = sm.regionA + s * SLAB;
-                        const double* Bs = sm.W + w2_slab_off(s) - (2 * s) * 128;
-#pragma unroll
-                        for (int kp = 0; kp < 2; kp++) {
-                            double2 a[4], b[4];
-#pragma unroll
-                            for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                            for (int ni = 0; ni < 4; ni++)
-                                if (4 * ds + 2 * kp <= 2 * ni + 1) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-                            for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-                                for (int ni = 0; ni < 4; ni++)
-                                    if (4 * ds + 2 * kp + hh <= 2 * ni + 1) {
-#pragma unroll
-                                        for (int mi = 0; mi < 4; mi++)
-                                            dmma(acc[mi][ni][0], acc[mi][ni][1], hh ? a[mi].y : a[mi].x, hh ? b[ni].y : b[ni].x);
-                                    }
-                        }
-                    }
-                    {
-                        double part[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                        for (int ni = 0; ni < 4; ni++) {
-                            const double z0 = sm.zs[32 * wc + 8 * ni + 2 * q], z1 = sm.zs[32 * wc + 8 * ni + 2 * q + 1];
-#pragma unroll
-                            for (int mi = 0; mi < 4; mi++) part[mi] = fma(acc[mi][ni][0], z0, fma(acc[mi][ni][1], z1, part[mi]));
-                        }
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++) {
-                            part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 1);
-                            part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 2);
-                            if (q == 0) sm.red[wc * SR + 32 * wr + 8 * mi + g] = part[mi];
-                        }
-                    }
+                    trsm_tile<Geo64>(acc, sm.regionA, sm.W, wr, wc, lane);       // L = S W^T
+                    lz_partials(acc, sm.zs, sm.red, SR, wr, wc, lane);
                     {
                         const int Ib = I + (wr >> 1);                // this warp's block row
                         store_tile_frag<false, SLAB2>(lbase + ((size_t)(Ib * (Ib - 1) / 2) + J) * BLK2, acc, 32 * (wr & 1), 32 * wc, lane);
