@@ -790,6 +790,46 @@ __device__ __forceinline__ void lz_partials(const double (&acc)[4][4][2], const 
     }
 }
 
+// ---------------------------------------------------------------- per-problem set-up shared by the kernels
+// exp(theta) and the derived constants (thread 0 of the CTA)
+__device__ __forceinline__ Hyp make_hyper(const double* th) {
+    Hyp h;
+    h.A = exp(th[0]); h.L = exp(th[1]); h.G = exp(th[2]); h.S = exp(th[3]); h.P = exp(th[4]);
+    h.hl = fmin(0.5 / h.L, DBL_MAX);                 // denormal L: d = 0 keeps exp(0), d != 0 underflows, as in the reference
+    h.thr = DBL_EPSILON * h.L;
+    return h;
+}
+// a non-finite or non-positive scale makes K non-finite or singular by construction: the reference returns -inf
+// (mingap2 < 0 flags a chunk with non-finite t or yerr)
+__device__ __forceinline__ bool hyper_ok(const Hyp& h, double mingap2) {
+    return h.A >= 0.0 && h.A <= DBL_MAX && h.L > 0.0 && h.L <= DBL_MAX && h.G >= 0.0 && h.G <= DBL_MAX &&
+           h.S >= 0.0 && h.S <= DBL_MAX && h.P > 0.0 && h.P <= DBL_MAX && mingap2 >= 0.0;
+}
+// per-point vectors of point i (i >= n: identity padding): clamped time stamp, sin / cos of the phase of t_i / P reduced in
+// double-double, diagonal noise, working copy of y
+__device__ __forceinline__ void point_vectors(int i, int n, const double* __restrict__ t, const double* __restrict__ y,
+                                              const double* __restrict__ yerr, const Hyp& h, double* vt, double* vs, double* vc,
+                                              double* vd, double* yw) {
+    double s = 0.0, c = 1.0, dg = 0.0, yy = 0.0;
+    const double ti = t[min(i, n - 1)];
+    if (i < n) {
+        const double hi = ti / h.P;
+        const double lo = fma(-hi, h.P, ti) / h.P;      // t/P = hi + lo to ~106 bits
+        const double ph = (hi - rint(hi)) + lo;          // |ph| <= 0.5 (+ tiny): sin^2 is invariant to the dropped integer
+        sincospi(ph, &s, &c);
+        const double e = sqrt(h.S + yerr[i] * yerr[i]);  // gprot/model.py:345-346
+        dg = e * e;
+        yy = y[i];
+    }
+    vt[i] = ti; vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
+}
+// lnlike from the two sums; non-finite -> -inf (gprot/model.py:356)
+__device__ __forceinline__ double finish_lnlike(double quad, double logdet, int n, bool failed) {
+    if (failed) return -INFINITY;
+    const double lnl = -0.5 * quad - 0.5 * (2.0 * logdet + (double)n * 1.8378770664093453);   // log(2 pi)
+    return (fabs(lnl) <= DBL_MAX) ? lnl : -INFINITY;
+}
+
 // ---------------------------------------------------------------- the kernel
 // CL = CTAs per problem.  CL > 1 launches thread-block clusters of CL CTAs that share one problem: every CTA forms the
 // diagonal block of a column (redundantly: same operands, same order, bitwise the same W and z_J -- the CTAs would
@@ -854,38 +894,16 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         const int T = (n + BS - 1) / BS;
         const int npad = T * BS;
 
-        if (tid == 0) {
-            Hyp h;
-            h.A = exp(th[0]); h.L = exp(th[1]); h.G = exp(th[2]); h.S = exp(th[3]); h.P = exp(th[4]);
-            h.hl = fmin(0.5 / h.L, DBL_MAX);                 // denormal L: d = 0 keeps exp(0), d != 0 underflows, as in the reference
-            h.thr = DBL_EPSILON * h.L;
-            sm.hyp = h;
-        }
+        if (tid == 0) sm.hyp = make_hyper(th);
         __syncthreads();
         const Hyp& h = sm.hyp;
-        const double mingap2 = prm.chunk_mingap2[chunk];            // < 0 flags a chunk with non-finite t or yerr
-        // a non-finite or non-positive scale makes K non-finite or singular by construction: the reference returns -inf
-        if (!(h.A >= 0.0 && h.A <= DBL_MAX && h.L > 0.0 && h.L <= DBL_MAX && h.G >= 0.0 && h.G <= DBL_MAX &&
-              h.S >= 0.0 && h.S <= DBL_MAX && h.P > 0.0 && h.P <= DBL_MAX && mingap2 >= 0.0)) {
+        const double mingap2 = prm.chunk_mingap2[chunk];
+        if (!hyper_ok(h, mingap2)) {
             if (tid == 0 && crank == 0) prm.prob_out[prob] = -INFINITY;
             continue;
         }
         const bool white_off = mingap2 < h.thr;
-        // per-point vectors: phase of t_i / P reduced in double-double, diagonal noise, working copy of y
-        for (int i = crank * NT + tid; i < npad; i += CL * NT) {
-            double s = 0.0, c = 1.0, dg = 0.0, yy = 0.0;
-            const double ti = t[min(i, n - 1)];
-            if (i < n) {
-                const double hi = ti / h.P;
-                const double lo = fma(-hi, h.P, ti) / h.P;      // t/P = hi + lo to ~106 bits
-                const double ph = (hi - rint(hi)) + lo;          // |ph| <= 0.5 (+ tiny): sin^2 is invariant to the dropped integer
-                sincospi(ph, &s, &c);
-                const double e = sqrt(h.S + yerr[i] * yerr[i]);  // gprot/model.py:345-346
-                dg = e * e;
-                yy = y[i];
-            }
-            vt[i] = ti; vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
-        }
+        for (int i = crank * NT + tid; i < npad; i += CL * NT) point_vectors(i, n, t, y, yerr, h, vt, vs, vc, vd, yw);
         if (CL > 1 && crank == 0) {                              // failure flag and per-column row counters of this problem
             int* const ctr0 = prm.cctr + (size_t)slot * (prm.tcap + 2);
             for (int i = tid; i < T + 1; i += NT) ctr0[i] = 0;
@@ -1097,15 +1115,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 for (int J = 0; J < T; J++) { quad += __ldcg(qcol + J); logdet += __ldcg(lcol + J); }
             }
         }
-        if (tid == 0 && crank == 0) {
-            double lnl;
-            if (failed) lnl = -INFINITY;
-            else {
-                lnl = -0.5 * quad - 0.5 * (2.0 * logdet + (double)n * 1.8378770664093453);   // log(2 pi)
-                if (!(fabs(lnl) <= DBL_MAX)) lnl = -INFINITY;                                   // gprot/model.py:356
-            }
-            prm.prob_out[prob] = lnl;
-        }
+        if (tid == 0 && crank == 0) prm.prob_out[prob] = finish_lnlike(quad, logdet, n, failed);
     }
 #ifdef GPROT_TIMING
     if (tid == 0 && blockIdx.x == 0 && prm.timing)

@@ -186,36 +186,17 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
         const int T = (n + BC - 1) / BC;
         const int npad = T * BC;
 
-        if (tid == 0) {
-            Hyp h;
-            h.A = exp(th[0]); h.L = exp(th[1]); h.G = exp(th[2]); h.S = exp(th[3]); h.P = exp(th[4]);
-            h.hl = fmin(0.5 / h.L, DBL_MAX);
-            h.thr = DBL_EPSILON * h.L;
-            sm.hyp = h;
-        }
+        if (tid == 0) sm.hyp = make_hyper(th);
         __syncthreads();
         const Hyp& h = sm.hyp;
         const double mingap2 = prm.chunk_mingap2[chunk];
-        if (!(h.A >= 0.0 && h.A <= DBL_MAX && h.L > 0.0 && h.L <= DBL_MAX && h.G >= 0.0 && h.G <= DBL_MAX &&
-              h.S >= 0.0 && h.S <= DBL_MAX && h.P > 0.0 && h.P <= DBL_MAX && mingap2 >= 0.0)) {
+        if (!hyper_ok(h, mingap2)) {
             if (tid == 0) prm.prob_out[prob] = -INFINITY;
             continue;
         }
         const bool white_off = mingap2 < h.thr;
-        for (int i = tid; i < npad + BC; i += NT2) {            // one block of slack: the last super tile may reach past npad
-            double s = 0.0, c = 1.0, dg = 0.0, yy = 0.0;
-            const double ti = t[min(i, n - 1)];
-            if (i < n) {
-                const double hi = ti / h.P;
-                const double lo = fma(-hi, h.P, ti) / h.P;
-                const double ph = (hi - rint(hi)) + lo;
-                sincospi(ph, &s, &c);
-                const double e = sqrt(h.S + yerr[i] * yerr[i]);
-                dg = e * e;
-                yy = y[i];
-            }
-            vt[i] = ti; vs[i] = s; vc[i] = c; vd[i] = dg; yw[i] = yy;
-        }
+        for (int i = tid; i < npad + BC; i += NT2)               // one block of slack: the last super tile may reach past npad
+            point_vectors(i, n, t, y, yerr, h, vt, vs, vc, vd, yw);
         __syncthreads();
 
         double logdet = 0.0, quad = 0.0;
@@ -309,15 +290,7 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
             fence_async();
             __syncthreads();
         }
-        if (tid == 0) {
-            double lnl;
-            if (failed) lnl = -INFINITY;
-            else {
-                lnl = -0.5 * quad - 0.5 * (2.0 * logdet + (double)n * 1.8378770664093453);
-                if (!(fabs(lnl) <= DBL_MAX)) lnl = -INFINITY;
-            }
-            prm.prob_out[prob] = lnl;
-        }
+        if (tid == 0) prm.prob_out[prob] = finish_lnlike(quad, logdet, n, failed);
     }
 }
 
