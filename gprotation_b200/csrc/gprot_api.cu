@@ -219,19 +219,13 @@ int choose_cluster(gprot_ctx* ctx, int nprob, int tmax) {
     return best;
 }
 
-// core: likelihood of the rows of theta selected by mask (NULL = all)
-int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* lc_id, const unsigned char* mask,
-                double* out, unsigned flags, cudaStream_t st) {
-    if (!ctx) return fail(nullptr, "null context");
-    if (B < 0 || (B > 0 && (!theta || !out))) return fail(ctx, "bad arguments");
-    if (B == 0) return 0;
-    if (ctx->lc_first_chunk.empty()) return fail(ctx, "no light curve registered");
-    CU(ctx, cudaSetDevice(ctx->device));
-    if (upload_arena(ctx)) return 1;
+// (theta row, chunk) problems of a launch, their per-row ranges for the chunk sum, and the queue order; uploaded to the
+// device unless the cached list of the previous identical call (same B, every row on light curve 0, no mask) is valid
+struct ProblemList { int nprob = 0, tmax = 0, nmax = 0; };
 
-    // ---- problem list
+int build_problem_list(gprot_ctx* ctx, int64_t B, const int32_t* lc_id, const unsigned char* mask, cudaStream_t st, ProblemList& pl) {
+    int& nprob = pl.nprob; int& tmax = pl.tmax; int& nmax = pl.nmax;
     const bool cacheable = (lc_id == nullptr && mask == nullptr);
-    int nprob = 0, tmax = 0, nmax = 0;
     if (cacheable && ctx->cache_B == B && ctx->cache_lc == 0) {
         nprob = ctx->cache_nprob;
         tmax = ctx->cache_tmax;
@@ -303,6 +297,150 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
         else ctx->cache_B = -1;
     }
 
+    return 0;
+}
+
+// which kernel, how many CTAs per problem, how many work slots and how much scratch each
+struct LaunchPlan { bool use64 = false; int cl = 1; int slots = 0; size_t stride = 0; int npad = 0; };
+
+int plan_launch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
+    const int nprob = pl.nprob, tmax = pl.tmax, nmax = pl.nmax;
+    if (!ctx->attr_set) {
+        for (int cl : {1, 2, 4, 8})
+            for (int ex = 0; ex < 2; ex++)
+                CU(ctx, cudaFuncSetAttribute((const void*)kernel_for(ex != 0, cl), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        ctx->attr_set = true;
+    }
+    query_clusters(ctx);
+    int cl = choose_cluster(ctx, nprob, tmax);
+    // Launches with more than one problem per SM and N < 1920 run the two-problems-per-SM kernel (gp_kernel64.cuh); the others
+    // keep one problem per SM (or per cluster).  gprot_set_cluster(64) / (1) force either.
+    const bool use64 = ctx->force_cluster == 64 ||
+                       (ctx->force_cluster == 0 && cl == 1 && nprob > ctx->num_sms && nmax < 1920);   // measured crossover
+    if (use64) cl = 1;
+    ctx->last_cluster = use64 ? 64 : cl;
+    if (use64 && !ctx->attr64_set) {
+        for (int ex = 0; ex < 2; ex++) {
+            const void* f = ex ? (const void*)k64::gp_lnlike64_kernel<true> : (const void*)k64::gp_lnlike64_kernel<false>;
+            CU(ctx, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k64::Smem2)));
+            CU(ctx, cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+        ctx->attr64_set = true;
+        if (getenv("GPROT_DEBUG")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k64::gp_lnlike64_kernel<false>, k64::NT2, sizeof(k64::Smem2));
+            fprintf(stderr, "[gprot] gp_lnlike64_kernel: %d CTAs per SM, %zu bytes of shared memory each\n", nb, sizeof(k64::Smem2));
+        }
+    }
+    const int t64 = (nmax + k64::BC - 1) / k64::BC;
+    lp.use64 = use64;
+    lp.cl = cl;
+    lp.slots = use64 ? std::min(nprob, 2 * ctx->num_sms) : std::min(nprob, ctx->max_clusters[cl]);   // one slot per resident CTA (group)
+    lp.stride = use64 ? std::max<size_t>((size_t)t64 * (t64 - 1) / 2, 1) * k64::BLK2
+                      : std::max<size_t>((size_t)tmax * (tmax - 1) / 2, 1) * BLKD;
+    lp.npad = use64 ? (t64 + 1) * k64::BC : tmax * BS;        // the 64-wide kernel reads one block past the end
+    return 0;
+}
+
+constexpr int TCAP = 1024;                                   // block columns the cluster kernels can track (N <= 131072)
+constexpr size_t WG_STRIDE = 2 * (size_t)(W_DOUBLES + BS) + 2 * TCAP;
+
+// factor scratch, per-point vectors and (cluster kernels) the W exchange buffers, grown on demand; may lower lp.slots to
+// what fits in device memory
+int ensure_scratch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
+    if (lp.stride > ctx->lslot_stride || lp.slots > ctx->lslots) {
+        CU(ctx, cudaDeviceSynchronize());
+        if (ctx->d_lscratch) CU(ctx, cudaFree(ctx->d_lscratch));
+        ctx->d_lscratch = nullptr;
+        const size_t s2 = std::max(lp.stride, ctx->lslot_stride);
+        int want = std::max(lp.slots, ctx->lslots);
+        size_t freeb = 0, totalb = 0;
+        CU(ctx, cudaMemGetInfo(&freeb, &totalb));
+        const size_t budget = (size_t)(0.85 * (double)freeb);
+        while (want > 1 && (size_t)want * s2 * 8 > budget) want--;
+        if ((size_t)want * s2 * 8 > budget) return fail(ctx, "not enough device memory for one factor scratch slot");
+        CU(ctx, cudaMalloc((void**)&ctx->d_lscratch, (size_t)want * s2 * 8));
+        ctx->lslot_stride = s2;
+        ctx->lslots = want;
+    }
+    lp.slots = std::min(lp.slots, ctx->lslots);
+    if (lp.npad > ctx->v_npad || lp.slots > ctx->vslots) {
+        CU(ctx, cudaDeviceSynchronize());
+        if (ctx->d_vscratch) CU(ctx, cudaFree(ctx->d_vscratch));
+        ctx->d_vscratch = nullptr;
+        const int np2 = std::max(lp.npad, ctx->v_npad);
+        const int want = std::max(ctx->lslots, ctx->vslots);
+        CU(ctx, cudaMalloc((void**)&ctx->d_vscratch, (size_t)want * 5 * np2 * 8));
+        ctx->v_npad = np2;
+        ctx->vslots = want;
+    }
+    if (lp.cl > 1) {
+        if (pl.tmax > TCAP) return fail(ctx, "problem too large for the cluster kernels");
+        if (lp.slots > ctx->cslots) {
+            CU(ctx, cudaDeviceSynchronize());
+            if (ctx->d_wg) CU(ctx, cudaFree(ctx->d_wg));
+            if (ctx->d_cctr) CU(ctx, cudaFree(ctx->d_cctr));
+            ctx->d_wg = nullptr; ctx->d_cctr = nullptr;
+            const int want = std::max(lp.slots, ctx->num_sms / 2);
+            CU(ctx, cudaMalloc((void**)&ctx->d_wg, (size_t)want * WG_STRIDE * 8));
+            CU(ctx, cudaMalloc((void**)&ctx->d_cctr, (size_t)want * (TCAP + 2) * 4));
+            ctx->cslots = want;
+        }
+    }
+    return 0;
+}
+
+// the likelihood kernel of the plan, bracketed by the timing events
+int launch_likelihood(gprot_ctx* ctx, const ProblemList& pl, const LaunchPlan& lp, const double* d_theta, unsigned flags, cudaStream_t st) {
+    Params prm;
+    prm.wg = ctx->d_wg; prm.wg_stride = WG_STRIDE; prm.cctr = ctx->d_cctr; prm.tcap = TCAP;
+    prm.t = ctx->d_t; prm.y = ctx->d_y; prm.yerr = ctx->d_yerr;
+    prm.chunk_off = ctx->d_chunk_off; prm.chunk_n = ctx->d_chunk_n; prm.chunk_mingap2 = ctx->d_chunk_mingap2;
+    prm.theta = d_theta;
+    prm.prob_theta = ctx->d_prob_theta; prm.prob_chunk = ctx->d_prob_chunk; prm.prob_out = ctx->d_prob_out;
+    prm.prob_order = ctx->use_order ? ctx->d_prob_order : nullptr;
+    prm.nprob = pl.nprob;
+    prm.counter = ctx->d_counter;
+    prm.lscratch = ctx->d_lscratch; prm.lslot_stride = ctx->lslot_stride;
+    prm.vscratch = ctx->d_vscratch; prm.npad_max = ctx->v_npad;
+    prm.timing = ctx->d_timing;
+    CU(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
+    CU(ctx, cudaEventRecord(ctx->ev0, st));
+    if (lp.use64) {
+        if (flags & GPROT_EXACT_KERNEL) k64::gp_lnlike64_kernel<true><<<lp.slots, k64::NT2, sizeof(k64::Smem2), st>>>(prm);
+        else                            k64::gp_lnlike64_kernel<false><<<lp.slots, k64::NT2, sizeof(k64::Smem2), st>>>(prm);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(lp.slots * lp.cl));
+        cfg.blockDim = dim3(NT);
+        cfg.dynamicSmemBytes = sizeof(Smem);
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)lp.cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = lp.cl > 1 ? 1 : 0;
+        CU(ctx, cudaLaunchKernelEx(&cfg, kernel_for((flags & GPROT_EXACT_KERNEL) != 0, lp.cl), prm));
+    }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->launches++;
+    return 0;
+}
+
+// core: likelihood of the rows of theta selected by mask (NULL = all)
+int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* lc_id, const unsigned char* mask,
+                double* out, unsigned flags, cudaStream_t st) {
+    if (!ctx) return fail(nullptr, "null context");
+    if (B < 0 || (B > 0 && (!theta || !out))) return fail(ctx, "bad arguments");
+    if (B == 0) return 0;
+    if (ctx->lc_first_chunk.empty()) return fail(ctx, "no light curve registered");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (upload_arena(ctx)) return 1;
+
+    ProblemList pl;
+    if (build_problem_list(ctx, B, lc_id, mask, st, pl)) return 1;
+    const int nprob = pl.nprob;
+
     // ---- theta / out on the device
     const double* d_theta = theta;
     if (!(flags & GPROT_THETA_ON_DEVICE)) {
@@ -317,112 +455,8 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
     }
 
     if (nprob > 0) {
-        // ---- work slots: one persistent CTA per SM, each with its own factor scratch
-        if (!ctx->attr_set) {
-            for (int cl : {1, 2, 4, 8})
-                for (int ex = 0; ex < 2; ex++)
-                    CU(ctx, cudaFuncSetAttribute((const void*)kernel_for(ex != 0, cl), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-            ctx->attr_set = true;
-        }
-        query_clusters(ctx);
-        int cl = choose_cluster(ctx, nprob, tmax);
-        // Launches with at least two problems per SM run the two-problems-per-SM kernel (gp_kernel64.cuh); smaller ones
-        // keep one problem per SM (or per cluster).  gprot_set_cluster(64) / (1) force either.
-        const bool use64 = ctx->force_cluster == 64 ||
-                           (ctx->force_cluster == 0 && cl == 1 && nprob > ctx->num_sms && nmax < 1920);   // measured crossover
-        if (use64) cl = 1;
-        ctx->last_cluster = use64 ? 64 : cl;
-        if (use64 && !ctx->attr64_set) {
-            for (int ex = 0; ex < 2; ex++) {
-                const void* f = ex ? (const void*)k64::gp_lnlike64_kernel<true> : (const void*)k64::gp_lnlike64_kernel<false>;
-                CU(ctx, cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(k64::Smem2)));
-                CU(ctx, cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            }
-            ctx->attr64_set = true;
-            if (getenv("GPROT_DEBUG")) {
-                int nb = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k64::gp_lnlike64_kernel<false>, k64::NT2, sizeof(k64::Smem2));
-                fprintf(stderr, "[gprot] gp_lnlike64_kernel: %d CTAs per SM, %zu bytes of shared memory each\n", nb, sizeof(k64::Smem2));
-            }
-        }
-        const int t64 = (nmax + k64::BC - 1) / k64::BC;
-        int slots = use64 ? std::min(nprob, 2 * ctx->num_sms) : std::min(nprob, ctx->max_clusters[cl]);   // one slot per resident CTA (group)
-        const size_t stride = use64 ? std::max<size_t>((size_t)t64 * (t64 - 1) / 2, 1) * k64::BLK2
-                                    : std::max<size_t>((size_t)tmax * (tmax - 1) / 2, 1) * BLKD;
-        const int npad = use64 ? (t64 + 1) * k64::BC : tmax * BS;        // the 64-wide kernel reads one block past the end
-        if (stride > ctx->lslot_stride || slots > ctx->lslots) {
-            CU(ctx, cudaDeviceSynchronize());
-            if (ctx->d_lscratch) CU(ctx, cudaFree(ctx->d_lscratch));
-            ctx->d_lscratch = nullptr;
-            const size_t s2 = std::max(stride, ctx->lslot_stride);
-            int want = std::max(slots, ctx->lslots);
-            size_t freeb = 0, totalb = 0;
-            CU(ctx, cudaMemGetInfo(&freeb, &totalb));
-            const size_t budget = (size_t)(0.85 * (double)freeb);
-            while (want > 1 && (size_t)want * s2 * 8 > budget) want--;
-            if ((size_t)want * s2 * 8 > budget) return fail(ctx, "not enough device memory for one factor scratch slot");
-            CU(ctx, cudaMalloc((void**)&ctx->d_lscratch, (size_t)want * s2 * 8));
-            ctx->lslot_stride = s2;
-            ctx->lslots = want;
-        }
-        slots = std::min(slots, ctx->lslots);
-        if (npad > ctx->v_npad || slots > ctx->vslots) {
-            CU(ctx, cudaDeviceSynchronize());
-            if (ctx->d_vscratch) CU(ctx, cudaFree(ctx->d_vscratch));
-            ctx->d_vscratch = nullptr;
-            const int np2 = std::max(npad, ctx->v_npad);
-            const int want = std::max(ctx->lslots, ctx->vslots);
-            CU(ctx, cudaMalloc((void**)&ctx->d_vscratch, (size_t)want * 5 * np2 * 8));
-            ctx->v_npad = np2;
-            ctx->vslots = want;
-        }
-        constexpr int TCAP = 1024;                                   // block columns (N <= 131072)
-        const size_t wg_stride = 2 * (size_t)(W_DOUBLES + BS) + 2 * TCAP;
-        if (cl > 1) {
-            if (tmax > TCAP) return fail(ctx, "problem too large for the cluster kernels");
-            if (slots > ctx->cslots) {
-                CU(ctx, cudaDeviceSynchronize());
-                if (ctx->d_wg) CU(ctx, cudaFree(ctx->d_wg));
-                if (ctx->d_cctr) CU(ctx, cudaFree(ctx->d_cctr));
-                ctx->d_wg = nullptr; ctx->d_cctr = nullptr;
-                const int want = std::max(slots, ctx->num_sms / 2);
-                CU(ctx, cudaMalloc((void**)&ctx->d_wg, (size_t)want * wg_stride * 8));
-                CU(ctx, cudaMalloc((void**)&ctx->d_cctr, (size_t)want * (TCAP + 2) * 4));
-                ctx->cslots = want;
-            }
-        }
-        Params prm;
-        prm.wg = ctx->d_wg; prm.wg_stride = wg_stride; prm.cctr = ctx->d_cctr; prm.tcap = TCAP;
-        prm.t = ctx->d_t; prm.y = ctx->d_y; prm.yerr = ctx->d_yerr;
-        prm.chunk_off = ctx->d_chunk_off; prm.chunk_n = ctx->d_chunk_n; prm.chunk_mingap2 = ctx->d_chunk_mingap2;
-        prm.theta = d_theta;
-        prm.prob_theta = ctx->d_prob_theta; prm.prob_chunk = ctx->d_prob_chunk; prm.prob_out = ctx->d_prob_out;
-        prm.prob_order = ctx->use_order ? ctx->d_prob_order : nullptr;
-        prm.nprob = nprob;
-        prm.counter = ctx->d_counter;
-        prm.lscratch = ctx->d_lscratch; prm.lslot_stride = ctx->lslot_stride;
-        prm.vscratch = ctx->d_vscratch; prm.npad_max = ctx->v_npad;
-        prm.timing = ctx->d_timing;
-        CU(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), st));
-        CU(ctx, cudaEventRecord(ctx->ev0, st));
-        if (use64) {
-            if (flags & GPROT_EXACT_KERNEL) k64::gp_lnlike64_kernel<true><<<slots, k64::NT2, sizeof(k64::Smem2), st>>>(prm);
-            else                            k64::gp_lnlike64_kernel<false><<<slots, k64::NT2, sizeof(k64::Smem2), st>>>(prm);
-        } else {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(slots * cl));
-            cfg.blockDim = dim3(NT);
-            cfg.dynamicSmemBytes = sizeof(Smem);
-            cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = cl > 1 ? 1 : 0;
-            CU(ctx, cudaLaunchKernelEx(&cfg, kernel_for((flags & GPROT_EXACT_KERNEL) != 0, cl), prm));
-        }
-        CU(ctx, cudaGetLastError());
-        CU(ctx, cudaEventRecord(ctx->ev1, st));
-        ctx->launches++;
+        LaunchPlan lp;
+        if (plan_launch(ctx, pl, lp) || ensure_scratch(ctx, pl, lp) || launch_likelihood(ctx, pl, lp, d_theta, flags, st)) return 1;
     }
     reduce_rows_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(ctx->d_prob_out, ctx->d_row_first, ctx->d_row_count, d_out, (long long)B);
     CU(ctx, cudaGetLastError());
