@@ -44,7 +44,6 @@ struct Hyp {
 struct Smem {
     double regionA[REGION_A];     // TMA stages | S_IJ staging (fragment-major) | diagonal workspace M (row-major)
     double W[W_DOUBLES];          // L_JJ^{-1}, B-operand fragments, rows c >= 16*slab only
-    double red[4 * BS];           // cross-warp partial sums of L_IJ z_J
     double zs[BS];                // z_J
     double yj[BS];                // ytilde_J
     double dinv[BS];              // 1 / diag(L_JJ)
@@ -125,6 +124,15 @@ __device__ __forceinline__ void tma_load(void* dst, const void* src, uint32_t by
 }
 // order generic-proxy accesses (st.global / ld.shared / st.shared) before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the same for shared memory only (re-use of a shared-memory region by TMA after generic reads / writes): does not
+// wait for this thread's global stores to drain
+__device__ __forceinline__ void fence_async_smem() {
+#ifdef GPROT_FULL_FENCE
+    asm volatile("fence.proxy.async;" ::: "memory");
+#else
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 // thread-block cluster: rank, barrier with release/acquire at cluster scope (orders global and shared::cluster
 // accesses of all CTAs of the cluster), store into a peer CTA's shared memory (DSMEM)
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -534,6 +542,15 @@ __device__ long long g_ts[16][8];
 #endif
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// barrier 2 + wr for the warps of warp row wr (immediate ids: a register id would make ptxas reserve all 16 barriers)
+__device__ __forceinline__ void row_sync(int wr, int count) {
+    switch (wr) {
+        case 0: asm volatile("bar.sync 2, %0;" ::"r"(count) : "memory"); break;
+        case 1: asm volatile("bar.sync 3, %0;" ::"r"(count) : "memory"); break;
+        case 2: asm volatile("bar.sync 4, %0;" ::"r"(count) : "memory"); break;
+        default: asm volatile("bar.sync 5, %0;" ::"r"(count) : "memory"); break;
+    }
+}
 
 // X = M(R, p) W_pp^T for one tile row, rewritten in place; rows above the pivot (R < p) also deliver the finished
 // tile of W^T to sm.W.  Returns the A fragment of -X.
@@ -714,79 +731,93 @@ __device__ __forceinline__ void diag_solve(SM& sm, int warp, int lane) {
     if (lane == 0) { sm.qpart[warp] = z2; sm.lpart[warp] = lg; }
 }
 
-// ---------------------------------------------------------------- TRSM as a GEMM with the inverse
-// acc <- S W^T for this warp's 32 x 32 tile: S = the staging block (A-operand slabs of 128 rows, written by
-// store_tile_frag), W = L_JJ^{-1} in B-operand layout (packed lower triangle, slab offsets from G).  k runs over
-// m <= c only; inside the two slabs that cross the diagonal the zero 8 x 4 sub-blocks of W are skipped.
-template <class G>
-__device__ __forceinline__ void trsm_tile(double (&acc)[4][4][2], const double* __restrict__ stag, const double* __restrict__ Wm,
-                                          int wr, int wc, int lane) {
+// ---------------------------------------------------------------- TRSM by substitution over 8-wide tile columns
+// X L_JJ^T = S solved the way LAPACK's dtrsm does, at the granularity of the DMMA tile:
+//     X_c = (S_c - sum_{m<c} X_m L_cm^T) W_cc^T ,   c = 0 .. NR-1,   W_cc = L_cc^{-1} (8 x 8 pivot-tile inverses only).
+// Round 1 multiplied by the explicit inverse of the whole diagonal block, whose backward error is eps * cond(L_JJ): up to
+// 40x further from the 80-bit truth than LAPACK at cond(K) ~ 1e10; 32-wide groups still lose a digit, 16- and 8-wide
+// ones are at LAPACK's level (tools/emulate_trsm.py, profiles/r02_trsm_emulation.log).
+//
+// Rows of X are independent, so every warp takes a strip of MT 8-row tiles across ALL columns of the block and runs the
+// substitution by itself: no barrier between warps, the dependent chain (tile c -> tile c+1) of one warp hides under
+// the trailing updates of the other warps of its scheduler.  sm.W holds the operator in B-operand layout (mix_operator):
+// W_cc in the diagonal tiles, L_JJ itself in the tiles below.  The strip lives in A-fragment layout (x[mt][c] = X[g][8c+q],
+// X[g][8c+q+4]) -- the register image of the fragment-major block, so each tile goes to global memory as one coalesced
+// 16-byte store per lane.
+
+// C fragment of an 8 x 8 tile (lane (g,q): [g][2q], [g][2q+1]) -> A fragment (lane (g,q): [g][q], [g][q+4])
+__device__ __forceinline__ void c_to_a(double c0, double c1, int lane, double& a0, double& a1) {
+    const int q = lane & 3, s0 = (lane & ~3) | (q >> 1), s1 = s0 | 2;
+    const double x0 = __shfl_sync(0xffffffffu, c0, s0), x1 = __shfl_sync(0xffffffffu, c1, s0);
+    const double y0 = __shfl_sync(0xffffffffu, c0, s1), y1 = __shfl_sync(0xffffffffu, c1, s1);
+    a0 = (q & 1) ? x1 : x0;
+    a1 = (q & 1) ? y1 : y0;
+}
+
+// Left-looking over the tile columns: only the strip (NR tiles x 2 registers), two partial sums and one B fragment
+// are live, and every finished tile leaves for global memory (and enters L_IJ z_J) at once, spread over the sweep.
+// x enters as the strip of S in A-fragment layout.  out[mt] = block base + 128 * (row group) + 2 * lane.
+template <class G, int MT, int SLABSTRIDE>
+__device__ __forceinline__ void trsm_strip(double2 (&x)[MT][G::NR], const double* __restrict__ Wm, const double* __restrict__ zs,
+                                           double* const (&out)[MT], double (&lz)[MT], int lane) {
+    const int q = lane & 3;
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++)
+    for (int mt = 0; mt < MT; mt++) lz[mt] = 0.0;
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) { acc[mi][ni][0] = 0.0; acc[mi][ni][1] = 0.0; }
-    for (int s = 0; s < 2 * wc; s++) {
-        const double* As = stag + s * SLAB;
-        const double* Bs = Wm + G::wslab(s) - (2 * s) * 128;
+    for (int c = 0; c < G::NR; c++) {
+        double u[MT][2][2];                                                  // -sum_{m<c} X_m L_cm^T, even / odd m apart
 #pragma unroll
-        for (int kp = 0; kp < 2; kp++) {
-            double2 a[4], b[4];
+        for (int mt = 0; mt < MT; mt++) { u[mt][0][0] = 0.0; u[mt][0][1] = 0.0; u[mt][1][0] = 0.0; u[mt][1][1] = 0.0; }
+        const double* brow = Wm + 128 * c + lane * 2;                        // tile (c, m) at brow + wslab(m/2) - 256 (m/2) + 64 (m&1)
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
+        for (int m = 0; m < c; m++) {
+            const double2 b = *reinterpret_cast<const double2*>(brow + G::wslab(m >> 1) - (m >> 1) * 256 + (m & 1) * 64);
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+            for (int mt = 0; mt < MT; mt++) {
+                dmma(u[mt][m & 1][0], u[mt][m & 1][1], -x[mt][m].x, b.x);
+                dmma(u[mt][m & 1][0], u[mt][m & 1][1], -x[mt][m].y, b.y);
+            }
+        }
+        const double2 w = *reinterpret_cast<const double2*>(brow + G::wslab(c >> 1) - (c >> 1) * 256 + (c & 1) * 64);   // W_cc
 #pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+        for (int mt = 0; mt < MT; mt++) {
+            double a0, a1;
+            c_to_a(u[mt][0][0] + u[mt][1][0], u[mt][0][1] + u[mt][1][1], lane, a0, a1);
+            a0 += x[mt][c].x;                                                // T_c = S_c - sum, as an A operand
+            a1 += x[mt][c].y;
+            double d0 = 0.0, d1 = 0.0;
+            dmma(d0, d1, a0, w.x);                                           // X_c = T_c W_cc^T
+            dmma(d0, d1, a1, w.y);
+            c_to_a(d0, d1, lane, a0, a1);                                    // A-fragment layout = the stored layout
+            x[mt][c] = make_double2(a0, a1);
+            *reinterpret_cast<double2*>(out[mt] + (c >> 1) * SLABSTRIDE + (c & 1) * 64) = x[mt][c];
+            lz[mt] = fma(a0, zs[8 * c + q], fma(a1, zs[8 * c + q + 4], lz[mt]));
         }
     }
 #pragma unroll
-    for (int ds = 0; ds < 2; ds++) {                   // the two slabs that cross the diagonal of W
-        const int s = 2 * wc + ds;
-        const double* As = stag + s * SLAB;
-        const double* Bs = Wm + G::wslab(s) - (2 * s) * 128;
-#pragma unroll
-        for (int kp = 0; kp < 2; kp++) {
-            double2 a[4], b[4];
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-            for (int ni = 0; ni < 4; ni++)
-                if (4 * ds + 2 * kp <= 2 * ni + 1) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++)
-                    if (4 * ds + 2 * kp + hh <= 2 * ni + 1) {
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++)
-                            dmma(acc[mi][ni][0], acc[mi][ni][1], hh ? a[mi].y : a[mi].x, hh ? b[ni].y : b[ni].x);
-                    }
-        }
+    for (int mt = 0; mt < MT; mt++) {                                        // (L_IJ z_J)[row g] in every lane of the row
+        lz[mt] += __shfl_xor_sync(0xffffffffu, lz[mt], 1);
+        lz[mt] += __shfl_xor_sync(0xffffffffu, lz[mt], 2);
     }
 }
 
-// sum over this warp's 32 columns of L_IJ z_J for its 32 rows -> red[wc * stride + row]
-__device__ __forceinline__ void lz_partials(const double (&acc)[4][4][2], const double* __restrict__ zs, double* red, int stride,
-                                            int wr, int wc, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-    double part[4] = {0.0, 0.0, 0.0, 0.0};
+// strip of S (rows 8 rg .. 8 rg + 7 of the 128-row staging block written by store_tile_frag) as A fragments
+template <int NCT>
+__device__ __forceinline__ void load_strip(double2 (&x)[NCT], const double* __restrict__ stag, int rg, int lane) {
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++) {
-        const double z0 = zs[32 * wc + 8 * ni + 2 * q], z1 = zs[32 * wc + 8 * ni + 2 * q + 1];
-#pragma unroll
-        for (int mi = 0; mi < 4; mi++) part[mi] = fma(acc[mi][ni][0], z0, fma(acc[mi][ni][1], z1, part[mi]));
-    }
-#pragma unroll
-    for (int mi = 0; mi < 4; mi++) {
-        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 1);
-        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 2);
-        if (q == 0) red[wc * stride + 32 * wr + 8 * mi + g] = part[mi];
+    for (int j = 0; j < NCT; j++) x[j] = *reinterpret_cast<const double2*>(stag + (j >> 1) * SLAB + rg * 128 + (j & 1) * 64 + lane * 2);
+}
+
+// sm.W after the diagonal sweep is the full inverse W = L_JJ^{-1} (used once more for z_J = W ytilde_J); its diagonal
+// 8 x 8 tiles are the inverses of the pivot tiles.  Overwrite the tiles below the diagonal with L_JJ itself (lower
+// triangle of the workspace M = sm.regionA, row-major): the operator trsm_strip expects.
+template <class G, class SM>
+__device__ __forceinline__ void mix_operator(SM& sm, int tid) {
+    constexpr int NB = 8 * G::NR;
+    const double* M = sm.regionA;
+    for (int d = tid; d < NB * NB; d += G::NTH) {
+        const int c = d / NB, m = d - c * NB;
+        if ((c >> 3) > (m >> 3)) sm.W[G::woff(c, m)] = M[c * G::LD + m];
     }
 }
 
@@ -921,6 +952,9 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         auto diag_block = [&](const int J, const int nextI) -> bool {
             const double* jrow = lbase + (size_t)(J * (J - 1) / 2) * BLKD;   // blocks (J, 0..J-1), contiguous
             const int niter = 8 * J;
+            const bool pf = nextI >= 0 && tid < 3 * BS;              // per-point values of block row nextI, parked on the way out
+            double pv = 0.0;
+            if (pf) pv = vt[(size_t)(tid >> 7) * prm.npad_max + nextI * BS + (tid & (BS - 1))];
             {
                 // the last block may be mostly identity padding: warp rows beyond the real points do no work at all
                 const int ractJ = (J == T - 1) ? ((n - J * BS + 31) >> 5) : 4;
@@ -960,8 +994,10 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             }
             if (sm.fail) return false;
             diag_solve<Geo128>(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
-            if (nextI >= 0) stage_points(sm.rowv, vt, prm.npad_max, nextI, tid);   // row side of the first block below
-            fence_async();
+            __syncthreads();                                            // every warp has read the full inverse
+            mix_operator<Geo128>(sm, tid);                              // L_JJ below the diagonal groups: two-level TRSM operator
+            if (pf) sm.rowv[tid] = pv;                                  // row side of the first block below
+            fence_async_smem();
             __syncthreads();
             TICK(5);
             if (tid == 0 && nextI >= 0) prologue<false>(sm, it, lbase + (size_t)(nextI * (nextI - 1) / 2) * BLKD, jrow, niter);
@@ -979,39 +1015,49 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 __syncthreads();
                 if (tid == 0) prologue<false>(sm, it, irow, jrow, niter);
             }
-                // Warp rows of the last block row that hold only identity padding skip everything but the barriers:
-                // their rows of L are never read by a warp that works (operands are consumed by the same warp row).
-                const int ract = (I == T - 1) ? ((n - I * BS + 31) >> 5) : 4;
-                const bool rowact = wr < ract;
-                if (rowact) {
-                    if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
-                    else                                synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
-                }
-                TICK(6);
-                accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, rowact);
-                __syncthreads();                                   // stages drained: regionA becomes the S_IJ staging block
-                TICK(7);
-                if (rowact) store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc
-                __syncthreads();
-                TICK(8);
-                if (rowact) {
-                    trsm_tile<Geo128>(acc, sm.regionA, sm.W, wr, wc, lane);      // L_IJ = S W^T
-                    lz_partials(acc, sm.zs, sm.red, BS, wr, wc, lane);           // ytilde_I -= L_IJ z_J, per warp column
-                    // stored as each warp finishes: warps with a short triangular product overlap their stores with the
-                    // others' DMMAs
-                    store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
-                }
-            if (nextI >= 0) stage_points(sm.rowv, vt, prm.npad_max, nextI, tid);   // row side of the next block
-            fence_async();
-            __syncthreads();                                   // staging reads done (regionA free again), partials visible
-            TICK(9);
-            if (tid == 0 && nextI >= 0)                        // next block's first slabs fly during its synthesis
-                prologue<false>(sm, it, lbase + (size_t)(nextI * (nextI - 1) / 2) * BLKD, jrow, niter);
-            if (tid < 32 * ract) {
-                const int r = tid;
-                yw[I * BS + r] -= (sm.red[r] + sm.red[BS + r]) + (sm.red[2 * BS + r] + sm.red[3 * BS + r]);
+            // Warp rows of the last block row that hold only identity padding skip everything but the barriers:
+            // their rows of L are never read by a warp that works (operands are consumed by the same warp row).
+            const int ract = (I == T - 1) ? ((n - I * BS + 31) >> 5) : 4;
+            const bool rowact = wr < ract;
+            double* const yrow = yw + I * BS + 8 * warp + g;       // this lane's row of the TRSM strip (rows 8 warp .. 8 warp + 7)
+            double ycur = 0.0;
+            // per-point values of the next block row: loaded now, parked in shared memory once sm.rowv is free (a global
+            // load in front of a barrier would put its latency on every warp's critical path)
+            const bool pf = nextI >= 0 && tid < 3 * BS;
+            double pv = 0.0;
+            if (pf) pv = vt[(size_t)(tid >> 7) * prm.npad_max + nextI * BS + (tid & (BS - 1))];
+            if (rowact) {
+                if (q == 0) ycur = *yrow;                          // needed at the very end: the load flies meanwhile
+                if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
+                else                                synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
             }
+            TICK(6);
+            accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, rowact);
+            __syncthreads();                                       // stages drained: regionA becomes the S_IJ staging block; sm.rowv is free
+            TICK(7);
+            if (pf) sm.rowv[tid] = pv;                             // row side of the next block
+            if (rowact) store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc, A-operand layout
+            __syncthreads();
+            TICK(8);
+            double2 xs[1][16];                                     // warp w: rows 8w .. 8w+7 of the block, all 128 columns
+            if (rowact) load_strip<16>(xs[0], sm.regionA, warp, lane);
+            fence_async_smem();
+            __syncthreads();                                       // every strip is in registers: regionA is free again
+            TICK(9);
+            if (tid == 0 && nextI >= 0)                            // next block's first slabs fly during the solve and its synthesis
+                prologue<false>(sm, it, lbase + (size_t)(nextI * (nextI - 1) / 2) * BLKD, jrow, niter);
             TICK(10);
+            if (rowact) {
+                double* const out[1] = {lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD + warp * 128 + lane * 2};
+                double lz[1];
+                trsm_strip<Geo128, 1, SLAB>(xs, sm.W, sm.zs, out, lz, lane);       // L_IJ L_JJ^T = S by substitution; stores L_IJ
+                if (q == 0) *yrow = ycur - lz[0];                  // ytilde_I -= L_IJ z_J (right-looking forward solve)
+            }
+            TICK(12);
+#ifdef GPROT_END_BARRIER
+            __syncthreads();
+#endif
+            // no barrier here: a warp that is done goes on to the next block's synthesis under the others' DMMAs
         };
 
         auto column_sums = [&](double& qs, double& ls) {       // fixed order: deterministic
