@@ -44,6 +44,7 @@ struct Hyp {
 struct Smem {
     double regionA[REGION_A];     // TMA stages | S_IJ staging (fragment-major) | diagonal workspace M (row-major)
     double W[W_DOUBLES];          // L_JJ^{-1}, B-operand fragments, rows c >= 16*slab only
+    double red[4 * BS];           // cross-warp partial sums of L_IJ z_J
     double zs[BS];                // z_J
     double yj[BS];                // ytilde_J
     double dinv[BS];              // 1 / diag(L_JJ)
@@ -150,17 +151,21 @@ __device__ __forceinline__ void dsmem_store_int(int* local, uint32_t peer, int v
 }
 
 // ---------------------------------------------------------------- layouts
-// Fragment-major operand layout.  A 128 x 16 slab is stored as [row group 16][k pair 2][lane 32][2]:
-// lane = (r&7)*4 + (k&3) is the DMMA A/B fragment lane, the pair holds k-quads 2*kp and 2*kp+1, so one
-// LDS.128 per lane fetches the fragments of two consecutive m8n8k4 steps, bank-conflict free.
+// Tile-major operand layout.  A 128 x 16 slab is stored as [row group 16][k tile 2][8][8]: 8 x 8 tiles, row-major inside.
+// Lane (g, q) = lane / 4, lane % 4 of a warp reads the 16 bytes at offset 2 * lane of a tile, i.e. elements [g][2q] and
+// [g][2q+1].  As an A (or B) operand of mma.sync.m8n8k4.f64 the first feeds k-slot q of one DMMA, the second k-slot q of
+// the next: the two DMMAs of a tile product cover columns {0,2,4,6} and {1,3,5,7} -- any split of k works as long as A
+// and B agree, and they always do because both come from this layout.  The same 16 bytes are ALSO the lane's C-fragment
+// of that tile ([g][2q], [g][2q+1]): accumulators go to memory, and come back as operands, with no shuffle in between
+// (staging of S_IJ, the TRSM strips, the stored blocks of L).  One LDS.128 per lane feeds two DMMAs, conflict-free.
 __device__ __forceinline__ int frag_off(int r, int kk) {   // r in [0,128), kk in [0,16)
-    return (r >> 3) * 128 + ((kk >> 3) & 1) * 64 + (((r & 7) << 2) + (kk & 3)) * 2 + ((kk >> 2) & 1);
+    return (r >> 3) * 128 + ((kk >> 3) & 1) * 64 + (r & 7) * 8 + (kk & 7);
 }
 __device__ __forceinline__ int w_slab_off(int s) { return 128 * s * (17 - s); }   // slab s keeps row groups 2s..15
 // position of W[c][m] (c >= 16 * (m / 16)) in the packed lower triangle sm.W: k-slab m/16, row group c/8
 __device__ __forceinline__ int w_off(int c, int m) {
     const int s = m >> 4;
-    return w_slab_off(s) + ((c >> 3) - 2 * s) * 128 + ((m >> 3) & 1) * 64 + (((c & 7) << 2) + (m & 3)) * 2 + ((m >> 2) & 1);
+    return w_slab_off(s) + ((c >> 3) - 2 * s) * 128 + ((m >> 3) & 1) * 64 + (c & 7) * 8 + (m & 7);
 }
 
 // Geometry of the diagonal-block sweep, shared by the two kernels (gp_kernel64.cuh has its own for 64 x 64 blocks)
@@ -172,28 +177,19 @@ struct Geo128 {
     __device__ static __forceinline__ int woff(int c, int m) { return w_off(c, m); }
 };
 
-// Store a warp's 32 x 32 C-fragment tile (acc[mi][ni][e] at row 8mi+g, col 8ni+2q+e) into a fragment-major
-// block at tile origin (row0, col0), optionally negated.  Lanes q and q^2 hold neighbouring doubles of the
-// destination, so one shuffle turns 32 scalar stores into 16 16-byte stores.
+// Store a warp's 32 x 32 C-fragment tile (acc[mi][ni][e] at row 8mi+g, col 8ni+2q+e) into a tile-major block at tile
+// origin (row0, col0), optionally negated: the lane's two accumulators of an 8 x 8 tile are 16 contiguous bytes.
 template <bool NEG, int SLABSTRIDE = SLAB>
 __device__ __forceinline__ void store_tile_frag(double* blk, const double (&acc)[4][4][2], int row0, int col0, int lane) {
-    const int g = lane >> 2, q = lane & 3, h = q >> 1;
 #pragma unroll
     for (int ni = 0; ni < 4; ni++) {
         const int c = col0 + 8 * ni;                       // multiple of 8
-        const int slab = c >> 4, kp = (c >> 3) & 1;
-        double* base = blk + slab * SLABSTRIDE + kp * 64 + ((g << 2) + ((q & 1) << 1) + h) * 2;
+        double* base = blk + (c >> 4) * SLABSTRIDE + ((c >> 3) & 1) * 64 + lane * 2;
 #pragma unroll
         for (int mi = 0; mi < 4; mi++) {
-            double v0 = acc[mi][ni][0], v1 = acc[mi][ni][1];
-            if (NEG) { v0 = -v0; v1 = -v1; }
-            const double send = h ? v0 : v1;
-            const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
-            double2 o;
-            o.x = h ? recv : v0;
-            o.y = h ? v1 : recv;
             const int rg = (row0 >> 3) + mi;
-            *reinterpret_cast<double2*>(base + rg * 128) = o;
+            *reinterpret_cast<double2*>(base + rg * 128) = NEG ? make_double2(-acc[mi][ni][0], -acc[mi][ni][1])
+                                                               : make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
     }
 }
@@ -393,72 +389,10 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
     return fma(y, e * fma(0.375, e, 0.5), y);
 }
 
-// Factor the 8 x 8 diagonal tile p of M (lower triangle) and invert it, one row per lane (lanes 8..31 mirror
-// lanes 0..7 so that shuffles stay warp-uniform).  Column j: the pivot is broadcast from lane j, every lane forms
-// 1/sqrt itself, scales its entry of the column and eliminates it from its row; the same elimination applied to
-// the rows of an identity yields the inverse (Gauss-Jordan on a triangular matrix), off the pivot's critical path.
-// (A register-resident variant without shuffles is faster in isolation -- 1.5k vs 2.1k cycles -- but needs ~110
-// registers on top of the kernel's live state and spills under the 128-register cap of a 512-thread CTA.)
-// Results: L_pp (lower, in M), W_pp^T (strict upper, in M), W_pp (sm.wt[buf], zero above the diagonal), 1/diag (sm.dinv).
-template <bool TO_W = false>
-__device__ __forceinline__ void tile8_factor(Smem& sm, int p, int buf, int lane) {
-    double* Mp = sm.regionA + (8 * p) * LDM + 8 * p;
-    const int a = lane & 7;
-    double row[8], inv[8];
-    {
-        const double2* src = reinterpret_cast<const double2*>(Mp + a * LDM);
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const double2 v = src[c];
-            row[2 * c] = v.x;
-            row[2 * c + 1] = v.y;
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 8; c++) inv[c] = (c == a) ? 1.0 : 0.0;
-    bool bad = false;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const double d = __shfl_sync(0xffffffffu, row[j], j);
-        if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
-        const double ri = rsqrt_pos(d);
-        double ljj = d * ri;
-        ljj = fma(fma(-ljj, ljj, d), 0.5 * ri, ljj);       // one Newton step on sqrt: <= 1 ulp
-        const double lj = (a == j) ? ljj : row[j] * ri;     // column j of L, one entry per lane (rows a >= j)
-        row[j] = lj;
-#pragma unroll
-        for (int b = j + 1; b < 8; b++) {                   // l[a][b] -= l[a][j] * l[b][j]   (used for a >= b)
-            const double cb = __shfl_sync(0xffffffffu, lj, b);
-            row[b] = fma(-lj, cb, row[b]);
-        }
-        // inverse rows: Y[j][:] *= 1/l_jj ; Y[a][:] -= l[a][j] * Y[j][:] for a > j   (Y starts as I, ends as L^-1)
-#pragma unroll
-        for (int c = 0; c <= j; c++) {
-            const double yj = __shfl_sync(0xffffffffu, inv[c] * ri, j);
-            inv[c] = (a == j) ? yj : ((a > j) ? fma(-lj, yj, inv[c]) : inv[c]);
-        }
-    }
-    if (lane < 8) {
-        double* wt = sm.wt + 64 * buf;
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const double w = (c <= a) ? inv[c] : 0.0;
-            wt[a * 8 + c] = w;                              // W_pp[a][c], zeros above the diagonal
-            if (c == a) sm.dinv[8 * p + a] = w;
-            if (TO_W) sm.W[w_off(8 * p + a, 8 * p + c)] = w;   // final position in the B-operand layout
-            else {
-                if (c < a) Mp[c * LDM + a] = w;             // strict upper of the tile: W_pp^T
-                if (c <= a) Mp[a * LDM + c] = row[c];       // L_pp
-            }
-        }
-    }
-    if (bad && lane == 0) sm.fail = 1;
-}
-
 // Pivot-tile factorisation without shuffles: every lane of the pivot warp holds the whole lower triangle and runs the
 // same elimination (the dependent chain is rsqrt -> scale -> one DFMA per pivot); lane b < 8 then forms column b of
 // the inverse by forward substitution.  Needs ~100 registers, which only the pivot warp's own loop can afford.
-// Same outputs as tile8_factor<true>: W_pp (sm.wt[buf] and its place in sm.W), 1/diag (sm.dinv).
+// Outputs: W_pp (sm.wt[buf] and its place in sm.W), 1/diag (sm.dinv).
 template <class G, class SM>
 __device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lane) {
     const double* Mp = sm.regionA + (8 * p) * G::LD + 8 * p;
@@ -690,9 +624,9 @@ __device__ __forceinline__ void diag_pad_identity(SM& sm, int c0, int tid) {
         const int cnt = (G::NR - 2 * s) * 128;
         double* dst = sm.W + G::wslab(s);
         for (int d = tid; d < cnt; d += G::NTH) {
-            const int rgrel = d >> 7, kp = (d >> 6) & 1, ln = (d >> 1) & 31, hh = d & 1;
-            const int c = 8 * (2 * s + rgrel) + (ln >> 2);
-            const int m = 16 * s + 4 * (2 * kp + hh) + (ln & 3);
+            const int rgrel = d >> 7, kp = (d >> 6) & 1;
+            const int c = 8 * (2 * s + rgrel) + ((d >> 3) & 7);
+            const int m = 16 * s + 8 * kp + (d & 7);
             if (c >= c0) dst[d] = (m == c) ? 1.0 : 0.0;
         }
     }
@@ -709,8 +643,8 @@ __device__ __forceinline__ void diag_solve(SM& sm, int warp, int lane) {
         const double* base = sm.W + G::wslab(s) + (warp - 2 * s) * 128 + lane * 2;
         const double2 f0 = *reinterpret_cast<const double2*>(base);
         const double2 f1 = *reinterpret_cast<const double2*>(base + 64);
-        const double* yk = sm.yj + 16 * s + q;
-        const double y0 = g == 0 ? yk[0] : 0.0, y1 = g == 0 ? yk[4] : 0.0, y2 = g == 0 ? yk[8] : 0.0, y3 = g == 0 ? yk[12] : 0.0;
+        const double* yk = sm.yj + 16 * s + 2 * q;                 // f0 = W[.][16s + 2q], [.. + 1]; f1 the same 8 further
+        const double y0 = g == 0 ? yk[0] : 0.0, y1 = g == 0 ? yk[1] : 0.0, y2 = g == 0 ? yk[8] : 0.0, y3 = g == 0 ? yk[9] : 0.0;
         dmma(za0, za1, f0.x, y0);
         dmma(zb0, zb1, f0.y, y1);
         dmma(za0, za1, f1.x, y2);
@@ -738,79 +672,100 @@ __device__ __forceinline__ void diag_solve(SM& sm, int warp, int lane) {
 // 40x further from the 80-bit truth than LAPACK at cond(K) ~ 1e10; 32-wide groups still lose a digit, 16- and 8-wide
 // ones are at LAPACK's level (tools/emulate_trsm.py, profiles/r02_trsm_emulation.log).
 //
-// Rows of X are independent, so every warp takes a strip of MT 8-row tiles across ALL columns of the block and runs the
-// substitution by itself: no barrier between warps, the dependent chain (tile c -> tile c+1) of one warp hides under
-// the trailing updates of the other warps of its scheduler.  sm.W holds the operator in B-operand layout (mix_operator):
-// W_cc in the diagonal tiles, L_JJ itself in the tiles below.  The strip lives in A-fragment layout (x[mt][c] = X[g][8c+q],
-// X[g][8c+q+4]) -- the register image of the fragment-major block, so each tile goes to global memory as one coalesced
-// 16-byte store per lane.
-
-// C fragment of an 8 x 8 tile (lane (g,q): [g][2q], [g][2q+1]) -> A fragment (lane (g,q): [g][q], [g][q+4])
-__device__ __forceinline__ void c_to_a(double c0, double c1, int lane, double& a0, double& a1) {
-    const int q = lane & 3, s0 = (lane & ~3) | (q >> 1), s1 = s0 | 2;
-    const double x0 = __shfl_sync(0xffffffffu, c0, s0), x1 = __shfl_sync(0xffffffffu, c1, s0);
-    const double y0 = __shfl_sync(0xffffffffu, c0, s1), y1 = __shfl_sync(0xffffffffu, c1, s1);
-    a0 = (q & 1) ? x1 : x0;
-    a1 = (q & 1) ? y1 : y0;
-}
-
-// Left-looking over the tile columns: only the strip (NR tiles x 2 registers), two partial sums and one B fragment
-// are live, and every finished tile leaves for global memory (and enters L_IJ z_J) at once, spread over the sweep.
-// x enters as the strip of S in A-fragment layout.  out[mt] = block base + 128 * (row group) + 2 * lane.
-template <class G, int MT, int SLABSTRIDE>
-__device__ __forceinline__ void trsm_strip(double2 (&x)[MT][G::NR], const double* __restrict__ Wm, const double* __restrict__ zs,
-                                           double* const (&out)[MT], double (&lz)[MT], int lane) {
-    const int q = lane & 3;
+// The block stays in the accumulators of the 4 x NG warp grid (warp (wr, wc): rows 32 wr.., columns 32 wc..), sixteen
+// independent 8 x 8 tiles per warp, so the DMMA pipe never waits on a dependent chain:
+//   * columns of OTHER warp columns (m < 4 wc): the finished X of warp (wr, c), c < wc, is read from the staging block
+//     as an A operand -- one 32-deep product per earlier warp column, after a named barrier of the warp row;
+//   * the warp's OWN four tile columns: substitution inside the registers.  In the tile-major layout a C fragment IS an
+//     A operand, so T_c feeds W_cc^T and X_c feeds the updates of the tiles to its right without leaving the registers;
+//     the four tile rows (mi) are independent chains.
+// sm.W holds the operator in B-operand layout (mix_operator): W_cc in the diagonal tiles, L_JJ itself in the tiles
+// below.  acc enters as -S and leaves as X = L_IJ.  stag: 128-row staging block, written with X for the warps to the right.
+template <class G, int NG>
+__device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __restrict__ stag, const double* __restrict__ Wm,
+                                             int wr, int wc, int lane) {
+#pragma unroll 1
+    for (int c = 0; c < NG; c++) {
+        if (wc == c) {
+            // ---- own columns: tiles 4c .. 4c+3 of the block, acc = -T
 #pragma unroll
-    for (int mt = 0; mt < MT; mt++) lz[mt] = 0.0;
+            for (int ni = 0; ni < 4; ni++) {
+                const int C = 4 * c + ni;                                                 // tile column of the block
+                const double* bcol = Wm + G::wslab(C >> 1) - (C >> 1) * 256 + (C & 1) * 64 + lane * 2;   // tile (R, C) at bcol + 128 R
+                const double2 w = *reinterpret_cast<const double2*>(bcol + 128 * C);       // W_CC
+                double xd[4][2];
 #pragma unroll
-    for (int c = 0; c < G::NR; c++) {
-        double u[MT][2][2];                                                  // -sum_{m<c} X_m L_cm^T, even / odd m apart
+                for (int mi = 0; mi < 4; mi++) {                                          // X = T W_CC^T = (-acc) W_CC^T
+                    xd[mi][0] = 0.0; xd[mi][1] = 0.0;
+                    dmma(xd[mi][0], xd[mi][1], -acc[mi][ni][0], w.x);
+                }
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) { u[mt][0][0] = 0.0; u[mt][0][1] = 0.0; u[mt][1][0] = 0.0; u[mt][1][1] = 0.0; }
-        const double* brow = Wm + 128 * c + lane * 2;                        // tile (c, m) at brow + wslab(m/2) - 256 (m/2) + 64 (m&1)
+                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], -acc[mi][ni][1], w.y);
 #pragma unroll
-        for (int m = 0; m < c; m++) {
-            const double2 b = *reinterpret_cast<const double2*>(brow + G::wslab(m >> 1) - (m >> 1) * 256 + (m & 1) * 64);
+                for (int mi = 0; mi < 4; mi++) { acc[mi][ni][0] = xd[mi][0]; acc[mi][ni][1] = xd[mi][1]; }
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) {
-                dmma(u[mt][m & 1][0], u[mt][m & 1][1], -x[mt][m].x, b.x);
-                dmma(u[mt][m & 1][0], u[mt][m & 1][1], -x[mt][m].y, b.y);
+                for (int n2 = ni + 1; n2 < 4; n2++) {                                     // -T_n2 += X_C L_{n2,C}^T
+                    const double2 b = *reinterpret_cast<const double2*>(bcol + 128 * (4 * c + n2));
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++) dmma(acc[mi][n2][0], acc[mi][n2][1], xd[mi][0], b.x);
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++) dmma(acc[mi][n2][0], acc[mi][n2][1], xd[mi][1], b.y);
+                }
+            }
+            if (c + 1 < NG) store_tile_frag<false>(stag, acc, 32 * wr, 32 * wc, lane);      // X for the warps to the right
+        }
+        if (c + 1 < NG) {
+            row_sync(wr, 32 * NG);
+            if (wc > c) {                                                                // -T_wc += X_c L_{wc,c}^T, 32 deep
+#pragma unroll
+                for (int ds = 0; ds < 2; ds++) {
+                    const int s = 2 * c + ds;
+                    const double* As = stag + s * SLAB;
+                    const double* Bs = Wm + G::wslab(s) - (2 * s) * 128;
+#pragma unroll
+                    for (int kp = 0; kp < 2; kp++) {
+                        double2 a[4], b[4];
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++) a[mi] = *reinterpret_cast<const double2*>(As + (4 * wr + mi) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) b[ni] = *reinterpret_cast<const double2*>(Bs + (4 * wc + ni) * 128 + kp * 64 + lane * 2);
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].x, b[ni].x);
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi].y, b[ni].y);
+                    }
+                }
             }
         }
-        const double2 w = *reinterpret_cast<const double2*>(brow + G::wslab(c >> 1) - (c >> 1) * 256 + (c & 1) * 64);   // W_cc
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-            double a0, a1;
-            c_to_a(u[mt][0][0] + u[mt][1][0], u[mt][0][1] + u[mt][1][1], lane, a0, a1);
-            a0 += x[mt][c].x;                                                // T_c = S_c - sum, as an A operand
-            a1 += x[mt][c].y;
-            double d0 = 0.0, d1 = 0.0;
-            dmma(d0, d1, a0, w.x);                                           // X_c = T_c W_cc^T
-            dmma(d0, d1, a1, w.y);
-            c_to_a(d0, d1, lane, a0, a1);                                    // A-fragment layout = the stored layout
-            x[mt][c] = make_double2(a0, a1);
-            *reinterpret_cast<double2*>(out[mt] + (c >> 1) * SLABSTRIDE + (c & 1) * 64) = x[mt][c];
-            lz[mt] = fma(a0, zs[8 * c + q], fma(a1, zs[8 * c + q + 4], lz[mt]));
-        }
-    }
-#pragma unroll
-    for (int mt = 0; mt < MT; mt++) {                                        // (L_IJ z_J)[row g] in every lane of the row
-        lz[mt] += __shfl_xor_sync(0xffffffffu, lz[mt], 1);
-        lz[mt] += __shfl_xor_sync(0xffffffffu, lz[mt], 2);
     }
 }
 
-// strip of S (rows 8 rg .. 8 rg + 7 of the 128-row staging block written by store_tile_frag) as A fragments
-template <int NCT>
-__device__ __forceinline__ void load_strip(double2 (&x)[NCT], const double* __restrict__ stag, int rg, int lane) {
+// sum over this warp's 32 columns of L_IJ z_J for its 32 rows -> red[wc * stride + row]
+__device__ __forceinline__ void lz_partials(const double (&acc)[4][4][2], const double* __restrict__ zs, double* red, int stride,
+                                            int wr, int wc, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int j = 0; j < NCT; j++) x[j] = *reinterpret_cast<const double2*>(stag + (j >> 1) * SLAB + rg * 128 + (j & 1) * 64 + lane * 2);
+    for (int ni = 0; ni < 4; ni++) {
+        const double z0 = zs[32 * wc + 8 * ni + 2 * q], z1 = zs[32 * wc + 8 * ni + 2 * q + 1];
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) part[mi] = fma(acc[mi][ni][0], z0, fma(acc[mi][ni][1], z1, part[mi]));
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++) {
+        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 1);
+        part[mi] += __shfl_xor_sync(0xffffffffu, part[mi], 2);
+        if (q == 0) red[wc * stride + 32 * wr + 8 * mi + g] = part[mi];
+    }
 }
 
 // sm.W after the diagonal sweep is the full inverse W = L_JJ^{-1} (used once more for z_J = W ytilde_J); its diagonal
 // 8 x 8 tiles are the inverses of the pivot tiles.  Overwrite the tiles below the diagonal with L_JJ itself (lower
-// triangle of the workspace M = sm.regionA, row-major): the operator trsm_strip expects.
+// triangle of the workspace M = sm.regionA, row-major): the operator trsm_inplace expects.
 template <class G, class SM>
 __device__ __forceinline__ void mix_operator(SM& sm, int tid) {
     constexpr int NB = 8 * G::NR;
@@ -1019,45 +974,36 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             // their rows of L are never read by a warp that works (operands are consumed by the same warp row).
             const int ract = (I == T - 1) ? ((n - I * BS + 31) >> 5) : 4;
             const bool rowact = wr < ract;
-            double* const yrow = yw + I * BS + 8 * warp + g;       // this lane's row of the TRSM strip (rows 8 warp .. 8 warp + 7)
-            double ycur = 0.0;
-            // per-point values of the next block row: loaded now, parked in shared memory once sm.rowv is free (a global
-            // load in front of a barrier would put its latency on every warp's critical path)
+            // per-point values of the next block row and this thread's entry of ytilde_I: loaded now, used at the end of the
+            // block (a global load in front of a barrier would put its latency on every warp's critical path)
             const bool pf = nextI >= 0 && tid < 3 * BS;
-            double pv = 0.0;
+            double pv = 0.0, ycur = 0.0;
             if (pf) pv = vt[(size_t)(tid >> 7) * prm.npad_max + nextI * BS + (tid & (BS - 1))];
+            if (tid < 32 * ract) ycur = yw[I * BS + tid];
             if (rowact) {
-                if (q == 0) ycur = *yrow;                          // needed at the very end: the load flies meanwhile
                 if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
                 else                                synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
             }
             TICK(6);
             accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, rowact);
-            __syncthreads();                                       // stages drained: regionA becomes the S_IJ staging block; sm.rowv is free
+            __syncthreads();                                       // stages drained: regionA becomes the X staging block; sm.rowv is free
             TICK(7);
             if (pf) sm.rowv[tid] = pv;                             // row side of the next block
-            if (rowact) store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc, A-operand layout
-            __syncthreads();
-            TICK(8);
-            double2 xs[1][16];                                     // warp w: rows 8w .. 8w+7 of the block, all 128 columns
-            if (rowact) load_strip<16>(xs[0], sm.regionA, warp, lane);
-            fence_async_smem();
-            __syncthreads();                                       // every strip is in registers: regionA is free again
-            TICK(9);
-            if (tid == 0 && nextI >= 0)                            // next block's first slabs fly during the solve and its synthesis
-                prologue<false>(sm, it, lbase + (size_t)(nextI * (nextI - 1) / 2) * BLKD, jrow, niter);
-            TICK(10);
             if (rowact) {
-                double* const out[1] = {lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD + warp * 128 + lane * 2};
-                double lz[1];
-                trsm_strip<Geo128, 1, SLAB>(xs, sm.W, sm.zs, out, lz, lane);       // L_IJ L_JJ^T = S by substitution; stores L_IJ
-                if (q == 0) *yrow = ycur - lz[0];                  // ytilde_I -= L_IJ z_J (right-looking forward solve)
+                trsm_inplace<Geo128, 4>(acc, sm.regionA, sm.W, wr, wc, lane);      // L_IJ L_JJ^T = S by substitution, acc: -S -> L_IJ
+                lz_partials(acc, sm.zs, sm.red, BS, wr, wc, lane);                 // L_IJ z_J, per warp column
+                // stored as each warp finishes: warps with little to do overlap their stores with the others' DMMAs
+                store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
             }
-            TICK(12);
-#ifdef GPROT_END_BARRIER
-            __syncthreads();
-#endif
-            // no barrier here: a warp that is done goes on to the next block's synthesis under the others' DMMAs
+            TICK(8);
+            fence_async_smem();
+            __syncthreads();                                       // staging reads done (regionA free again), partials visible
+            TICK(9);
+            if (tid == 0 && nextI >= 0)                            // next block's first slabs fly during its synthesis
+                prologue<false>(sm, it, lbase + (size_t)(nextI * (nextI - 1) / 2) * BLKD, jrow, niter);
+            if (tid < 32 * ract)                                   // ytilde_I -= L_IJ z_J (right-looking forward solve)
+                yw[I * BS + tid] = ycur - ((sm.red[tid] + sm.red[BS + tid]) + (sm.red[2 * BS + tid] + sm.red[3 * BS + tid]));
+            TICK(10);
         };
 
         auto column_sums = [&](double& qs, double& ls) {       // fixed order: deterministic

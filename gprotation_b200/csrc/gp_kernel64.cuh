@@ -27,6 +27,7 @@ constexpr int SR = 128;           // rows of the super tile
 struct Smem2 {
     double regionA[REGION2];
     double W[W2_DOUBLES];
+    double red[2 * SR];           // partial sums of L z_J per warp column
     double zs[BC];
     double yj[BC];
     double dinv[BC];
@@ -46,7 +47,7 @@ struct Smem2 {
 __device__ __forceinline__ int w2_slab_off(int s) { return 128 * s * (9 - s); }      // slab s keeps row groups 2s..7
 __device__ __forceinline__ int w2_off(int c, int m) {
     const int s = m >> 4;
-    return w2_slab_off(s) + ((c >> 3) - 2 * s) * 128 + ((m >> 3) & 1) * 64 + (((c & 7) << 2) + (m & 3)) * 2 + ((m >> 2) & 1);
+    return w2_slab_off(s) + ((c >> 3) - 2 * s) * 128 + ((m >> 3) & 1) * 64 + (c & 7) * 8 + (m & 7);
 }
 
 // per-point values (t, sin, cos) of `cnt` points starting at point p0
@@ -263,47 +264,36 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                 const double* a1 = lbase + (size_t)((I + 1) * I / 2) * BLK2;
                 const int ract = min(4, (n - I * BC + 31) >> 5);            // warp rows that hold real points
                 const bool rowact = wr < ract;
-                double* const yrow = yw + I * BC + 16 * warp + g;           // this lane's rows of the TRSM strip: 16 warp + g, + 8
-                // per-point values (t, sin, cos) of the next super tile: loaded now, parked once sm.rowv is free
+                // per-point values (t, sin, cos) of the next super tile and this thread's entry of ytilde: loaded now, used
+                // at the end of the super tile (no global-load latency in front of a barrier)
                 const int In = I + 2;
-                double pv0 = 0.0, pv1 = 0.0;
+                double pv0 = 0.0, pv1 = 0.0, ycur = 0.0;
                 if (In < T) {
-                    pv0 = vt[(size_t)(tid >> 7) * prm.npad_max + In * BC + (tid & (SR - 1))];                       // t | first half of sin
+                    pv0 = vt[(size_t)(tid >> 7) * prm.npad_max + In * BC + (tid & (SR - 1))];                       // t | sin
                     if (tid < SR) pv1 = vt[(size_t)2 * prm.npad_max + In * BC + tid];                              // cos
-                    else pv1 = 0.0;
                 }
-                double ycur0 = 0.0, ycur1 = 0.0;
+                if (tid < 32 * ract) ycur = yw[I * BC + tid];
                 if (rowact) {
-                    if (q == 0) { ycur0 = yrow[0]; ycur1 = yrow[8]; }       // needed at the very end: the loads fly meanwhile
                     if (I * BC + SR <= n && !white_off) synth_tile<EXACT, false, SR, BC>(acc, sm, 32 * wr, 32 * wc, I * BC + 32 * wr, J * BC + 32 * wc, n, vd, white_off, lane);
                     else                                synth_tile<EXACT, true, SR, BC>(acc, sm, 32 * wr, 32 * wc, I * BC + 32 * wr, J * BC + 32 * wc, n, vd, white_off, lane);
                 }
                 accumulate2<false>(sm, acc, it, a0, a1, jrow, niter, two, wr, wc, lane, rowact);
-                __syncthreads();                                   // stages drained: regionA becomes the staging block; sm.rowv is free
+                __syncthreads();                                   // stages drained: regionA becomes the X staging block; sm.rowv is free
                 if (In < T) {
-                    sm.rowv[tid] = pv0;                            // tid < 128: t, else sin (which = tid >> 7, stride SR = 128)
+                    sm.rowv[tid] = pv0;                            // tid < 128: t, else sin (stride SR = 128)
                     if (tid < SR) sm.rowv[2 * SR + tid] = pv1;
                 }
-                if (rowact) store_tile_frag<true>(sm.regionA, acc, 32 * wr, 32 * wc, lane);   // S = -acc, 128-row A slabs
-                __syncthreads();
-                double2 xs[2][8];                                  // warp w: rows 16w .. 16w+15 of the super tile, all 64 columns
                 if (rowact) {
-                    load_strip<8>(xs[0], sm.regionA, 2 * warp, lane);
-                    load_strip<8>(xs[1], sm.regionA, 2 * warp + 1, lane);
+                    trsm_inplace<Geo64, 2>(acc, sm.regionA, sm.W, wr, wc, lane);     // L L_JJ^T = S by substitution, acc: -S -> L
+                    lz_partials(acc, sm.zs, sm.red, SR, wr, wc, lane);
+                    const int Ib = I + (wr >> 1);                  // this warp's block row
+                    store_tile_frag<false, SLAB2>(lbase + ((size_t)(Ib * (Ib - 1) / 2) + J) * BLK2, acc, 32 * (wr & 1), 32 * wc, lane);
                 }
                 fence_async_smem();
-                __syncthreads();                                   // every strip is in registers: regionA is free again
+                __syncthreads();
                 if (tid == 0 && In < T)
                     prologue2<false>(sm, it, lbase + (size_t)(In * (In - 1) / 2) * BLK2, lbase + (size_t)((In + 1) * In / 2) * BLK2, jrow, niter, In + 1 < T);
-                if (rowact) {
-                    const int Ib = I + (warp >> 2);                // this warp's block row
-                    double* const blk = lbase + ((size_t)(Ib * (Ib - 1) / 2) + J) * BLK2 + lane * 2;
-                    double* const out[2] = {blk + ((2 * warp) & 7) * 128, blk + ((2 * warp + 1) & 7) * 128};
-                    double lz[2];
-                    trsm_strip<Geo64, 2, SLAB2>(xs, sm.W, sm.zs, out, lz, lane);     // L L_JJ^T = S by substitution; stores L
-                    if (q == 0) { yrow[0] = ycur0 - lz[0]; yrow[8] = ycur1 - lz[1]; }   // ytilde -= L z_J
-                }
-                // no barrier here: a warp that is done goes on to the next super tile's synthesis under the others' DMMAs
+                if (tid < 32 * ract) yw[I * BC + tid] = ycur - (sm.red[tid] + sm.red[SR + tid]);   // ytilde -= L z_J
             }
             __threadfence();
             fence_async();

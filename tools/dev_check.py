@@ -15,15 +15,14 @@ def make_lc(N, seed=0):
     return t, y, yerr
 
 def unpack_block(buf):
-    """fragment-major 128x128 block -> row-major"""
+    """tile-major 128x128 block ([slab 8][row group 16][k tile 2][8][8]) -> row-major"""
     B = np.zeros((128, 128))
     d = np.arange(16384)
     slab, r = d // 2048, d % 2048
     rg, r2 = r // 128, r % 128
     kp, r3 = r2 // 64, r2 % 64
-    ln, hh = r3 // 2, r3 % 2
-    row = rg * 8 + ln // 4
-    col = slab * 16 + 4 * (2 * kp + hh) + ln % 4
+    row = rg * 8 + r3 // 8
+    col = slab * 16 + 8 * kp + r3 % 8
     B[row, col] = buf
     return B
 

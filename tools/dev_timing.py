@@ -10,8 +10,8 @@ from gprotation_b200.synth import synthetic_lightcurve
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 names = ["setup", "diag synth", "diag accumulate", "diag M write", "diag factor+inverse", "W convert + z", "offdiag synth",
-         "offdiag accumulate", "staging store + barrier", "strip load + barrier", "TMA prologue issue", "column fence",
-         "TRSM substitution + stores", "-", "-", "queue pop"]
+         "offdiag accumulate", "TRSM + L z partials + store L", "barrier", "TMA prologue issue + y update", "column fence",
+         "-", "-", "-", "queue pop"]
 eng = GPEngine(0)
 t, y, yerr, _ = synthetic_lightcurve(1, N, kind="harmonic")
 eng.register_lc(t, y, yerr)

@@ -3,8 +3,73 @@
 #include "../gprotation_b200/csrc/gp_kernel.cuh"
 using namespace gprot;
 
+
 // ---- the in-place rank-8 sweep the kernel used before the warp-specialised version (kept here as the A/B baseline)
 // one rank-8 update task of step p: tile (R, C) -= X(R) * L(C, p)^T
+// round-1 pivot-tile routine (one row per lane, shuffles), kept here for the comparison only
+// Factor the 8 x 8 diagonal tile p of M (lower triangle) and invert it, one row per lane (lanes 8..31 mirror
+// lanes 0..7 so that shuffles stay warp-uniform).  Column j: the pivot is broadcast from lane j, every lane forms
+// 1/sqrt itself, scales its entry of the column and eliminates it from its row; the same elimination applied to
+// the rows of an identity yields the inverse (Gauss-Jordan on a triangular matrix), off the pivot's critical path.
+// (A register-resident variant without shuffles is faster in isolation -- 1.5k vs 2.1k cycles -- but needs ~110
+// registers on top of the kernel's live state and spills under the 128-register cap of a 512-thread CTA.)
+// Results: L_pp (lower, in M), W_pp^T (strict upper, in M), W_pp (sm.wt[buf], zero above the diagonal), 1/diag (sm.dinv).
+template <bool TO_W = false>
+__device__ __forceinline__ void tile8_factor(Smem& sm, int p, int buf, int lane) {
+    double* Mp = sm.regionA + (8 * p) * LDM + 8 * p;
+    const int a = lane & 7;
+    double row[8], inv[8];
+    {
+        const double2* src = reinterpret_cast<const double2*>(Mp + a * LDM);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double2 v = src[c];
+            row[2 * c] = v.x;
+            row[2 * c + 1] = v.y;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) inv[c] = (c == a) ? 1.0 : 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const double d = __shfl_sync(0xffffffffu, row[j], j);
+        if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
+        const double ri = rsqrt_pos(d);
+        double ljj = d * ri;
+        ljj = fma(fma(-ljj, ljj, d), 0.5 * ri, ljj);       // one Newton step on sqrt: <= 1 ulp
+        const double lj = (a == j) ? ljj : row[j] * ri;     // column j of L, one entry per lane (rows a >= j)
+        row[j] = lj;
+#pragma unroll
+        for (int b = j + 1; b < 8; b++) {                   // l[a][b] -= l[a][j] * l[b][j]   (used for a >= b)
+            const double cb = __shfl_sync(0xffffffffu, lj, b);
+            row[b] = fma(-lj, cb, row[b]);
+        }
+        // inverse rows: Y[j][:] *= 1/l_jj ; Y[a][:] -= l[a][j] * Y[j][:] for a > j   (Y starts as I, ends as L^-1)
+#pragma unroll
+        for (int c = 0; c <= j; c++) {
+            const double yj = __shfl_sync(0xffffffffu, inv[c] * ri, j);
+            inv[c] = (a == j) ? yj : ((a > j) ? fma(-lj, yj, inv[c]) : inv[c]);
+        }
+    }
+    if (lane < 8) {
+        double* wt = sm.wt + 64 * buf;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const double w = (c <= a) ? inv[c] : 0.0;
+            wt[a * 8 + c] = w;                              // W_pp[a][c], zeros above the diagonal
+            if (c == a) sm.dinv[8 * p + a] = w;
+            if (TO_W) sm.W[w_off(8 * p + a, 8 * p + c)] = w;   // final position in the B-operand layout
+            else {
+                if (c < a) Mp[c * LDM + a] = w;             // strict upper of the tile: W_pp^T
+                if (c <= a) Mp[a * LDM + c] = row[c];       // L_pp
+            }
+        }
+    }
+    if (bad && lane == 0) sm.fail = 1;
+}
+
+
 __device__ __forceinline__ void tile8_update(Smem& sm, int p, int R, int C, int g, int q) {
     double* M = sm.regionA;
     const int P0 = 8 * p;
