@@ -201,17 +201,18 @@ def _worker_json(argv, timeout=900):
 
 # ------------------------------------------------------------------------------------------ parity of the bench star
 def _parity_eval(args):
-    """(oracle lnlike, cond(K)) of one proposal; above cond 1e8 also the unblocked fp64 and 80-bit evaluations."""
+    """(oracle lnlike, cond(K)) of one proposal; above cond 1e8, or where the CUDA value misses 1e-9, also the unblocked
+    fp64 and the 80-bit evaluations."""
     import ctypes
 
     from oracle import gp_oracle as o
 
-    th, t, y, yerr = args
+    th, t, y, yerr, got = args
     ref = o.lnlike_function(th, t, y, yerr)
     ev = np.linalg.eigvalsh(o.kernel_matrix(th, t, yerr))
     cond = float(ev[-1] / ev[0]) if ev[0] > 0 else float("inf")
     ld = c64 = None
-    if cond > 1e8 and np.isfinite(ref):
+    if np.isfinite(ref) and (cond > 1e8 or abs(got - ref) > 1e-9 * abs(ref)):
         lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libgp_oracle.so"))
         a = [np.ascontiguousarray(v, dtype=np.float64) for v in (th, t, y, yerr)]
         for name in ("gp_oracle_lnlike_ld", "gp_oracle_lnlike_f64"):
@@ -231,7 +232,7 @@ def parity_worker(path):
 
     d = np.load(path)
     t, y, yerr, _ = synthetic_lightcurve(int(d["seed"]), int(d["n"]), kind=str(d["kind"]))
-    work = [(th, t, y, yerr) for th in d["theta"]]
+    work = [(th, t, y, yerr, g) for th, g in zip(d["theta"], d["got"])]
     cores = len(os.sched_getaffinity(0))
     with mp.get_context("fork").Pool(min(cores, len(work)), initializer=_cpu_init) as pool:
         res = pool.map(_parity_eval, work, chunksize=1)
@@ -249,7 +250,7 @@ def parity_block(seed, n, theta, got, rows=64, kind="gp"):
     idx = np.unique(np.linspace(0, B - 1, min(rows, B)).astype(int))
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "parity_in.npz")
-        np.savez(path, seed=seed, n=n, kind=kind, theta=theta[idx])
+        np.savez(path, seed=seed, n=n, kind=kind, theta=theta[idx], got=np.asarray(got)[idx])
         r = _worker_json(["--parity-worker", path])
     if "failed" in r:
         return {"rows": 0, "failed": r["failed"]}
@@ -259,12 +260,19 @@ def parity_block(seed, n, theta, got, rows=64, kind="gp"):
     fin = np.isfinite(ref)
     rel = np.abs(g[fin] - ref[fin]) / np.abs(ref[fin])
     lo = cond[fin] <= 1e8
-    tail = []
+    tail = []                                                   # rows above cond 1e8 or missing the flat 1e-9
     for k in np.nonzero(fin)[0]:
         if r["ld"][k] is not None:
             ld = r["ld"][k]
-            tail.append({"row": int(idx[k]), "cond": float(cond[k]), "gpu_vs_80bit": abs(g[k] - ld) / abs(ld),
+            tail.append({"row": int(idx[k]), "cond": float(cond[k]), "rel_err_vs_oracle": abs(g[k] - ref[k]) / abs(ref[k]),
+                         "gpu_vs_80bit": abs(g[k] - ld) / abs(ld),
                          "lapack_vs_80bit": abs(ref[k] - ld) / abs(ld), "unblocked_f64_vs_80bit": abs(r["c64"][k] - ld) / abs(ld)})
+    rule = [bool(rel[j] <= 1e-9) for j in range(len(rel))]
+    fk = list(np.nonzero(fin)[0])
+    for v in tail:                                             # the tests' rule: flat 1e-9, else within 3x of the worse CPU fp64 answer
+        j = fk.index(list(idx).index(v["row"]))
+        if not rule[j]:
+            rule[j] = bool(v["gpu_vs_80bit"] <= max(1e-9, 3 * max(v["lapack_vs_80bit"], v["unblocked_f64_vs_80bit"])))
     return {"rows": int(len(idx)), "finite_rows": int(fin.sum()),
             "finiteness_agrees": bool(np.array_equal(np.isfinite(g), fin)),
             "max_rel_err": float(rel.max()) if rel.size else None,
@@ -272,9 +280,9 @@ def parity_block(seed, n, theta, got, rows=64, kind="gp"):
             "max_cond": float(cond[fin].max()) if fin.any() else None,
             "rows_cond_le_1e8": int(lo.sum()), "max_rel_err_cond_le_1e8": float(rel[lo].max()) if lo.any() else None,
             "frac_within_1e-9_cond_le_1e8": float(np.mean(rel[lo] <= 1e-9)) if lo.any() else None,
-            "tail_cond_gt_1e8": tail,
-            "tail_gpu_within_3x_of_worse_cpu_fp64": bool(all(v["gpu_vs_80bit"] <= 3 * max(v["lapack_vs_80bit"], v["unblocked_f64_vs_80bit"], 1e-12)
-                                                            for v in tail)),
+            "rows_cond_gt_1e8_or_missing_1e-9": tail,
+            "rows_passing_test_rule": int(sum(rule)),
+            "test_rule": "|gpu-oracle| <= 1e-9 |oracle|, else |gpu-80bit| <= max(1e-9, 3 max(|lapack-80bit|, |unblocked_f64-80bit|))",
             "against": "oracle/gp_oracle.py (dense NumPy/LAPACK restatement of the george path; george itself not installable: parity unpinned)"}
 
 
@@ -340,7 +348,7 @@ def run_config3(eng, torch, dist, rank, world, local, peak_tf, args):
 
         with tempfile.TemporaryDirectory() as tmp:       # one row against the oracle (an N=8192 dense factorisation on the host)
             path = os.path.join(tmp, "c3.npz")
-            np.savez(path, seed=1, n=n, kind="harmonic", theta=th[:1])
+            np.savez(path, seed=1, n=n, kind="harmonic", theta=th[:1], got=res[:1])
             r = _worker_json(["--parity-worker", path])
         if "failed" not in r and r["ref"][0] is not None:
             out["row0_rel_err_vs_oracle"] = abs(res[0] - r["ref"][0]) / abs(r["ref"][0])

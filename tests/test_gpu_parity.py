@@ -1,12 +1,24 @@
 """Parity of the CUDA path against the oracle, through the C ABI (gprot_lnlike_batch / gprot_lnpost_batch).
 
-Tolerance (north star): |lnlike_gpu - lnlike_oracle| <= 1e-9 * |lnlike_oracle| in fp64 on prior-typical draws.
-Both sides are fp64 factorisations with different summation orders, so their difference grows like
-eps * cond(K); the bound is therefore written as  TOL(cond) = 1e-9 * max(1, cond / 1e7)  and every test
-asserts it with the condition number of the actual matrix (prior draws have cond ~1e2..1e6; the tail above
-1e7 is covered by the scaled bound and by comparison against the 80-bit long-double evaluation).
+Rule (north star: 1e-9 relative on lnlike, fp64), the same for every row of every test, whatever its condition number:
+
+    |lnlike_gpu - lnlike_oracle| <= 1e-9 * |lnlike_oracle|                                    (flat, no cond scaling)
+
+and, only where that fails, the row must be one where fp64 itself cannot do better -- demonstrated per row with the
+80-bit long-double evaluation (oracle/gp_oracle_ld.c) and TWO independent fp64 CPU evaluations, LAPACK's blocked dpotrf
+(the oracle) and an unblocked scalar Cholesky in george's operation order:
+
+    |lnlike_gpu - lnlike_80bit| <= max(1e-9 * |lnlike|, 3 * max(|oracle - 80bit|, |unblocked_f64 - 80bit|))
+
+i.e. the CUDA path is never further from the truth than 3x the worse of two correct fp64 CPU algorithms.  This branch
+is needed above cond(K) ~ 1e7..1e8 (eps * cond > 1e-9: e.g. the unblocked CPU Cholesky is 1.5e-9 off at cond 3e8) and
+for results that are small because quad and logdet cancel (n = 127 row of test_sizes_and_padding_edges: |lnlike| = 40
+against terms of 1200, LAPACK itself 1.7e-9 from the 80-bit value at cond 1.9e7).  profiles/r02_parity_campaign_*.json
+counts how often each branch is taken over 4000 random evaluations.
 """
+import ctypes
 import math
+import os
 
 import numpy as np
 import pytest
@@ -16,25 +28,55 @@ from gprotation_b200.synth import synthetic_lightcurve
 
 pytestmark = pytest.mark.gpu
 
-
-def tol(cond):
-    return 1e-9 * np.maximum(1.0, np.asarray(cond) / 1e7)
-
-
-def cond_of(th, t, yerr):
-    ev = np.linalg.eigvalsh(o.kernel_matrix(th, t, yerr))
-    return ev[-1] / ev[0]
+TOL = 1e-9
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_clib = None
 
 
-def check(got, ref, conds, what="", scale=None):
-    """|got - ref| <= TOL(cond) * scale, scale = |ref| unless given.  lnlike = -1/2 (quad + logdet + n ln 2pi) is a sum
-    of terms of either sign; where they cancel (|lnlike| much smaller than its terms) no fp64 factorisation can hold
-    1e-9 relative to the result, and the callers that sweep many shapes pass scale = max(|ref|, size of the terms)."""
-    got, ref = np.asarray(got), np.asarray(ref)
+def _c_oracle(which, th, t, y, e):
+    global _clib
+    if _clib is None:
+        _clib = ctypes.CDLL(os.path.join(_ROOT, "oracle", "_build", "libgp_oracle.so"))
+        for f in (_clib.gp_oracle_lnlike_f64, _clib.gp_oracle_lnlike_ld):
+            f.restype = ctypes.c_double
+            f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    th, t, y, e = (np.ascontiguousarray(a, dtype=np.float64) for a in (th, t, y, e))
+    fn = _clib.gp_oracle_lnlike_ld if which == "ld" else _clib.gp_oracle_lnlike_f64
+    return fn(th.ctypes.data, len(t), t.ctypes.data, y.ctypes.data, e.ctypes.data)
+
+
+def truths(th, t, y, yerr, chunks=None):
+    """(80-bit value, unblocked fp64 value) of lnlike, summed over the chunk list."""
+    parts = [np.arange(len(t))] if chunks is None else chunks
+    return (sum(_c_oracle("ld", th, t[c], y[c], yerr[c]) for c in parts),
+            sum(_c_oracle("f64", th, t[c], y[c], yerr[c]) for c in parts))
+
+
+def cond_of(th, t, yerr, chunks=None):
+    """cond(K) of the matrix the row factorises (the worst chunk of a chunked light curve)."""
+    worst = 0.0
+    for c in ([np.arange(len(t))] if chunks is None else chunks):
+        ev = np.linalg.eigvalsh(o.kernel_matrix(th, t[c], yerr[c]))
+        worst = max(worst, ev[-1] / ev[0] if ev[0] > 0 else np.inf)
+    return worst
+
+
+def check(got, ref, conds, what="", scale=None, truth=None):
+    """The rule of the module docstring.  truth(i) -> (80-bit value, unblocked fp64 value) of row i, evaluated only for
+    rows that miss the flat bound.  The error is relative to |ref| unless `scale` is given (callers that sweep many
+    shapes pass max(|ref|, size of the terms lnlike is the cancelling sum of)).  conds is reported on failure."""
+    got, ref, conds = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64), np.asarray(conds, dtype=np.float64)
     assert np.array_equal(np.isfinite(got), np.isfinite(ref)), what
-    m = np.isfinite(ref)
-    rel = np.abs(got[m] - ref[m]) / (np.abs(ref[m]) if scale is None else np.asarray(scale)[m])
-    assert np.all(rel <= tol(np.asarray(conds)[m])), (what, rel, tol(np.asarray(conds)[m]))
+    sc = np.abs(ref) if scale is None else np.asarray(scale, dtype=np.float64)
+    rel = np.full(len(ref), 0.0)
+    for i in np.nonzero(np.isfinite(ref))[0]:
+        rel[i] = abs(got[i] - ref[i]) / sc[i]
+        if rel[i] <= TOL:
+            continue
+        assert truth is not None, (what, "row %d misses 1e-9 (%.2e, cond %.2e) and no 80-bit yardstick was supplied" % (i, rel[i], conds[i]))
+        ld, f64 = truth(i)
+        bound = max(TOL * sc[i], 3.0 * max(abs(ref[i] - ld), abs(f64 - ld)))
+        assert abs(got[i] - ld) <= bound, (what, i, "gpu-80bit %.2e > bound %.2e, cond %.2e" % (abs(got[i] - ld) / sc[i], bound / sc[i], conds[i]))
     return rel
 
 
@@ -46,9 +88,9 @@ def test_golden_fixtures(engine, golden, name, exact):
     engine.unregister_all()
     lc = engine.register_lc(t, y, yerr, chunks=o.split_chunks(len(t), None if cs < 0 else cs))
     got = engine.lnlike_batch(golden[name + "_theta"], lc_id=lc, exact=exact)
-    check(got, golden[name + "_lnlike"], golden[name + "_cond"], name)
+    ld, f64 = golden[name + "_lnlike_c_ld"], golden[name + "_lnlike_c_f64"]
+    check(got, golden[name + "_lnlike"], golden[name + "_cond"], name, truth=lambda i: (ld[i], f64[i]))
     # and against the long-double evaluation: the GPU is no further from the truth than fp64 rounding allows
-    ld = golden[name + "_lnlike_c_ld"]
     assert np.all(np.abs(got - ld) <= 1e-13 * np.maximum(1e4, golden[name + "_cond"]) * np.abs(ld))
 
 
@@ -62,7 +104,8 @@ def test_sizes_and_padding_edges(engine, n):
     ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th])
     conds = [cond_of(x, t, yerr) for x in th]
     for exact in (False, True):
-        check(engine.lnlike_batch(th, lc_id=lc, exact=exact), ref, conds, "n=%d exact=%d" % (n, exact))
+        check(engine.lnlike_batch(th, lc_id=lc, exact=exact), ref, conds, "n=%d exact=%d" % (n, exact),
+              truth=lambda i: truths(th[i], t, y, yerr))
 
 
 def test_analytic_n1_n2(engine):
@@ -98,9 +141,8 @@ def test_chunked_equals_sum_of_chunks_and_ragged_batch(engine):
     for x, i in zip(th, ids):
         _, t, y, yerr, chunks = lcs[i]
         ref.append(o.lnlike(x, t, y, yerr, chunks))
-        parts = chunks if chunks is not None else [np.arange(len(t))]
-        conds.append(max(cond_of(x, t[c], yerr[c]) for c in parts))
-    check(got, ref, conds, "ragged")
+        conds.append(cond_of(x, t, yerr, chunks))
+    check(got, ref, conds, "ragged", truth=lambda i: truths(th[i], *lcs[ids[i]][1:]))
     # LightCurve.x_list route gives the same numbers as explicit index chunks
     from gprotation_b200.lc import LightCurve
 
@@ -124,7 +166,7 @@ def test_failure_rows_are_minus_inf_and_do_not_poison_the_batch(engine):
     assert got[1] == -np.inf and got[3] == -np.inf and got[4] == -np.inf
     assert not np.any(np.isnan(got))
     good = [0, 2, 5]
-    check(got[good], ref[good], [cond_of(th[i], t, yerr) for i in good])
+    check(got[good], ref[good], [cond_of(th[i], t, yerr) for i in good], "good rows", truth=lambda k: truths(th[good[k]], t, y, yerr))
 
 
 def test_coincident_time_stamps_fire_the_white_kernel_off_diagonal(engine):
@@ -141,7 +183,7 @@ def test_coincident_time_stamps_fire_the_white_kernel_off_diagonal(engine):
     ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th])
     conds = [cond_of(x, t, yerr) for x in th]
     for exact in (False, True):
-        check(engine.lnlike_batch(th, lc_id=lc, exact=exact), ref, conds, "dups")
+        check(engine.lnlike_batch(th, lc_id=lc, exact=exact), ref, conds, "dups", truth=lambda i: truths(th[i], t, y, yerr))
 
 
 def test_unsorted_input_and_scaling_property_full_size(engine):
@@ -164,9 +206,13 @@ def test_unsorted_input_and_scaling_property_full_size(engine):
     scal = engine.lnlike_batch(th2, lc_id=s)
     ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th[:4]])
     conds = np.array([cond_of(x, t, yerr) for x in th])
-    check(base[:4], ref, conds[:4], "n2048 vs oracle")
-    assert np.all(np.abs(perm - base) <= 10 * tol(conds) * np.abs(base))
-    assert np.all(np.abs(scal - (base - n * math.log(c))) <= 10 * tol(conds) * np.abs(base))
+    check(base[:4], ref, conds[:4], "n2048 vs oracle", truth=lambda i: truths(th[i], t, y, yerr))
+    # two evaluations of mathematically identical problems: each within the tolerance of the common value
+    lo = conds <= 1e7
+    assert lo.sum() >= 4
+    assert np.all(np.abs(perm - base)[lo] <= 2 * TOL * np.abs(base)[lo])
+    assert np.all(np.abs(scal - (base - n * math.log(c)))[lo] <= 2 * TOL * np.abs(base)[lo])
+    assert np.all(np.abs(perm - base) <= 1e-15 * conds * np.abs(base) + 2 * TOL * np.abs(base))    # the tail: a few eps * cond
 
 
 def test_full_config_batch_is_deterministic_and_consistent(engine):
@@ -184,7 +230,7 @@ def test_full_config_batch_is_deterministic_and_consistent(engine):
     assert np.array_equal(part, full[:296])
     idx = [0, 500, 1023]
     ref = np.array([o.lnlike_function(th[i], t, y, yerr) for i in idx])
-    check(full[idx], ref, [cond_of(th[i], t, yerr) for i in idx], "config-2 sample")
+    check(full[idx], ref, [cond_of(th[i], t, yerr) for i in idx], "config-2 sample", truth=lambda k: truths(th[idx[k]], t, y, yerr))
     assert np.all(np.isfinite(full) | (full == -np.inf))
 
 
@@ -202,7 +248,8 @@ def test_lnpost_batch_masks_rows_outside_the_prior(engine):
     assert ll[2] == -np.inf and ll[5] == -np.inf
     ok = np.isfinite(lp)
     ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th[ok]])
-    check(ll[ok], ref, [cond_of(x, t, yerr) for x in th[ok]])
+    tok = th[ok]
+    check(ll[ok], ref, [cond_of(x, t, yerr) for x in tok], "lnpost rows", truth=lambda k: truths(tok[k], t, y, yerr))
 
 
 def test_model_surface_is_a_drop_in(engine):
@@ -272,7 +319,8 @@ def test_cluster_variants_are_bitwise_identical(engine, n, chunksize):
         ref = np.array([o.lnlike(x, t, y, yerr, chunks) for x in th])
         m = np.isfinite(ref)
         assert np.array_equal(np.isfinite(base), m)
-        assert np.all(np.abs(base[m] - ref[m]) <= 1e-8 * np.abs(ref[m]))
+        conds = [cond_of(x, t, yerr, chunks) if f else 1.0 for x, f in zip(th, m)]
+        check(base, ref, conds, "cluster base n=%d" % n, truth=lambda i: truths(th[i], t, y, yerr, chunks))
         for cl in (2, 4, 8):
             engine.set_cluster(cl)
             for exact in (False, True):
@@ -302,9 +350,13 @@ def test_cluster_auto_choice(engine):
     assert np.array_equal(small, mid[:16])                 # one-CTA and cluster kernels agree to the bit
     big = engine.lnlike_batch(th, lc_id=lc)                # more than one problem per SM, N < 1920: two problems per SM
     assert engine.last_cluster() == 64
-    m = np.isfinite(big[:16])
-    assert np.array_equal(m, np.isfinite(small))
-    assert np.all(np.abs(big[:16][m] - small[m]) <= 2e-5 * np.abs(small[m]))     # different blocking: ~eps * cond apart
+    # the two blockings (128- and 64-wide) are two fp64 algorithms: each is held to the oracle by the same rule
+    ref = np.array([o.lnlike_function(x, t, y, yerr) for x in th[:16]])
+    conds = [cond_of(x, t, yerr) if np.isfinite(r) else 1.0 for x, r in zip(th[:16], ref)]
+    tr = lambda i: truths(th[i], t, y, yerr)  # noqa: E731
+    check(small, ref, conds, "cluster kernel", truth=tr)
+    check(big[:16], ref, conds, "two-per-SM kernel", truth=tr)
+    m = np.isfinite(ref)
     assert np.median(np.abs(big[:16][m] - small[m]) / np.abs(small[m])) <= 1e-11
 
 
@@ -349,6 +401,8 @@ def test_long_baseline_stress_shape(engine):
     n, c = 8192, 3.0
     t, y, yerr, _ = synthetic_lightcurve(7, n, kind="harmonic")
     th = o.sample_from_prior(6, seed=55)
+    th[:, 0] = np.linspace(-14.0, -12.0, 6)              # A / (2 S) ~ 1: cond(K) ~ 1e4 at N = 8192, so the flat 1e-9 applies to
+    th[:, 3] = -13.5                                     # every row (the eigenvalues of six 8192^2 matrices would take minutes)
     th2 = th.copy()
     th2[:, 0] += 2 * math.log(c)
     th2[:, 3] += 2 * math.log(c)
@@ -366,10 +420,9 @@ def test_long_baseline_stress_shape(engine):
     finally:
         engine.set_cluster(0)
     ref = o.lnlike_function(th[0], t, y, yerr)
-    assert abs(base[0] - ref) <= 1e-9 * abs(ref)
-    m = np.isfinite(base)
-    assert m.sum() >= 4
-    assert np.all(np.abs(scal[m] - (base[m] - n * math.log(c))) <= 1e-8 * np.abs(base[m]))
+    assert abs(base[0] - ref) <= TOL * abs(ref)
+    assert np.all(np.isfinite(base))
+    assert np.all(np.abs(scal - (base - n * math.log(c))) <= 2 * TOL * np.abs(base))     # two evaluations of the same value
 
 
 def test_multi_star_sweep_shape(engine):
@@ -391,13 +444,14 @@ def test_multi_star_sweep_shape(engine):
         part = allrows[s * W:(s + 1) * W]
         m = np.isfinite(alone)
         assert np.array_equal(m, np.isfinite(part))
-        # two different blockings of the same fp64 factorisation differ like any two fp64 algorithms, by ~eps * cond
-        # (prior draws reach cond 4e10 here: 2e-6); this is the coarse check, the cond-scaled one against the oracle follows
-        assert np.all(np.abs(alone[m] - part[m]) <= 2e-5 * np.maximum(np.abs(alone[m]), 1.0))
         assert np.median(np.abs(alone[m] - part[m]) / np.maximum(np.abs(alone[m]), 1.0)) <= 1e-12
-        k = s * W + 17
-        ref = o.lnlike_function(th[k], *lcs[s])
-        assert abs(allrows[k] - ref) <= 1e-9 * max(1.0, cond_of(th[k], lcs[s][0], lcs[s][2]) / 1e7) * abs(ref)
+        # the two blockings are two fp64 algorithms: both are held to the oracle by the same rule on a sample of rows
+        ks = [s * W + j for j in (3, 17, 40, 63)]
+        ref = np.array([o.lnlike_function(th[k], *lcs[s]) for k in ks])
+        conds = [cond_of(th[k], lcs[s][0], lcs[s][2]) if np.isfinite(r) else 1.0 for k, r in zip(ks, ref)]
+        tr = lambda i: truths(th[ks[i]], *lcs[s])  # noqa: E731
+        check(allrows[ks], ref, conds, "sweep rows of star %d" % s, truth=tr)
+        check(alone[[k - s * W for k in ks]], ref, conds, "star %d alone" % s, truth=tr)
 
 
 def test_repeated_launches_are_bitwise_stable(engine):
@@ -444,7 +498,8 @@ def test_every_ragged_tail(engine, k):
         for cl in (1, 2):
             engine.set_cluster(cl)
             got = engine.lnlike_batch(thetas, lc_id=rows)
-            check(got, ref, conds, "ragged tails k=%d cl=%d" % (k, cl), scale=np.maximum(np.abs(ref), terms))
+            check(got, ref, conds, "ragged tails k=%d cl=%d" % (k, cl), scale=np.maximum(np.abs(ref), terms),
+                  truth=lambda i: truths(thetas[i], *cases[i // len(th)][1:]))
     finally:
         engine.set_cluster(0)
 
@@ -463,7 +518,8 @@ def test_two_problems_per_sm_kernel_parity(engine, golden):
             for exact in (False, True):
                 got = engine.lnlike_batch(golden[name + "_theta"], lc_id=lc, exact=exact)
                 assert engine.last_cluster() == 64
-                check(got, golden[name + "_lnlike"], golden[name + "_cond"], name)
+                check(got, golden[name + "_lnlike"], golden[name + "_cond"], name,
+                      truth=lambda i: (golden[name + "_lnlike_c_ld"][i], golden[name + "_lnlike_c_f64"][i]))
         # ragged tails: n = 64 k + r
         th = o.sample_from_prior(3, seed=17)
         engine.unregister_all()
@@ -480,7 +536,8 @@ def test_two_problems_per_sm_kernel_parity(engine, golden):
         terms = np.array([0.5 * (abs(np.linalg.slogdet(o.kernel_matrix(x, c[1], c[3]))[1]) + len(c[1]) * math.log(2 * math.pi))
                           for c in cases for x in th])
         got = engine.lnlike_batch(thetas, lc_id=rows)
-        check(got, ref, conds, "64-wide ragged tails", scale=np.maximum(np.abs(ref), terms))
+        check(got, ref, conds, "64-wide ragged tails", scale=np.maximum(np.abs(ref), terms),
+              truth=lambda i: truths(thetas[i], *cases[i // len(th)][1:]))
         assert np.array_equal(engine.lnlike_batch(thetas, lc_id=rows), got)          # deterministic
         # failing rows and coincident stamps
         t, y, yerr, truth = synthetic_lightcurve(77, 330, baseline=200.0, kind="harmonic")
@@ -497,7 +554,7 @@ def test_two_problems_per_sm_kernel_parity(engine, golden):
             got = engine.lnlike_batch(th, lc_id=lc)
             ref = np.array([o.lnlike_function(x, tt, y, yerr) for x in th])
             conds = [cond_of(x, tt, yerr) if np.isfinite(r) else 1.0 for x, r in zip(th, ref)]
-            check(got, ref, conds, "failure / coincident rows")
+            check(got, ref, conds, "failure / coincident rows", truth=lambda i: truths(th[i], tt, y, yerr))
             assert got[3] == -np.inf
     finally:
         engine.set_cluster(0)

@@ -17,17 +17,20 @@ from gprotation_b200.synth import synthetic_lightcurve  # noqa: E402
 import ctypes  # noqa: E402
 
 _c = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_build", "libgp_oracle.so"))
-_c.gp_oracle_lnlike_ld.restype = ctypes.c_double
-_c.gp_oracle_lnlike_ld.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+for _f in (_c.gp_oracle_lnlike_ld, _c.gp_oracle_lnlike_f64):
+    _f.restype = ctypes.c_double
+    _f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
 
 
-def lnlike_long_double(x, t, y, yerr, chunks):
-    """80-bit evaluation (oracle/gp_oracle_ld.c), summed over the chunks: the yardstick for both fp64 answers."""
+def lnlike_long_double(x, t, y, yerr, chunks, fn=None):
+    """80-bit evaluation (oracle/gp_oracle_ld.c), summed over the chunks: the yardstick for both fp64 answers.
+    fn = _c.gp_oracle_lnlike_f64: the unblocked fp64 Cholesky in george's operation order (a second fp64 opinion)."""
+    fn = fn or _c.gp_oracle_lnlike_ld
     x = np.ascontiguousarray(x, dtype=np.float64)
     tot = 0.0
     for c in ([np.arange(len(t))] if chunks is None else chunks):
         tt, yy, ee = (np.ascontiguousarray(a[c], dtype=np.float64) for a in (t, y, yerr))
-        tot += _c.gp_oracle_lnlike_ld(x.ctypes.data, len(tt), tt.ctypes.data, yy.ctypes.data, ee.ctypes.data)
+        tot += fn(x.ctypes.data, len(tt), tt.ctypes.data, yy.ctypes.data, ee.ctypes.data)
     return tot
 
 
@@ -55,21 +58,29 @@ for case in range(ncases):
         got = eng.lnlike_batch(th, lc_id=lc, exact=exact)
         for k, x in enumerate(th):
             ref = o.lnlike(x, t, y, yerr, chunks)
-            cond = 0.0
+            cond, terms = 0.0, 0.0
             for c in ([np.arange(n)] if chunks is None else chunks):          # worst chunk
                 ev = np.linalg.eigvalsh(o.kernel_matrix(x, t[c], yerr[c]))
                 cond = max(cond, float(ev[-1] / ev[0]) if ev[0] > 0 else float("inf"))
-            row = dict(n=n, chunksize=cs, kind=kind, cluster=cl, exact=exact, ref=float(ref), got=float(got[k]), cond=cond)
+                if ev[0] > 0:                                                 # size of the terms lnlike is the (cancelling) sum of
+                    terms += 0.5 * (abs(float(np.sum(np.log(ev)))) + len(c) * math.log(2 * math.pi))
+            row = dict(n=n, chunksize=cs, kind=kind, cluster=cl, exact=exact, ref=float(ref), got=float(got[k]), cond=cond,
+                       scale=max(abs(float(ref)), terms) if math.isfinite(ref) else 0.0)
             if math.isfinite(ref) and abs(got[k] - ref) > 1e-10 * abs(ref):
                 ld = lnlike_long_double(x, t, y, yerr, chunks)
+                f64 = lnlike_long_double(x, t, y, yerr, chunks, fn=_c.gp_oracle_lnlike_f64)
                 row["gpu_vs_long_double"] = abs(got[k] - ld) / abs(ld)
                 row["oracle_vs_long_double"] = abs(ref - ld) / abs(ld)
+                row["unblocked_f64_vs_long_double"] = abs(f64 - ld) / abs(ld)
             rows.append(row)
 eng.set_cluster(0)
 fin = [r for r in rows if math.isfinite(r["ref"])]
 rel = np.array([abs(r["got"] - r["ref"]) / abs(r["ref"]) for r in fin])
 conds = np.array([r["cond"] for r in fin])
+rel_sc = np.array([abs(r["got"] - r["ref"]) / r["scale"] for r in fin])
 chk = [r for r in fin if "gpu_vs_long_double" in r]
+tail = [r for r in chk if r["cond"] > 1e8]
+tail_ratio = np.array([r["gpu_vs_long_double"] / max(r["oracle_vs_long_double"], r["unblocked_f64_vs_long_double"], 1e-300) for r in tail])
 mism = [r for r in rows if math.isfinite(r["ref"]) != math.isfinite(r["got"])]
 worst = sorted(fin, key=lambda r: -abs(r["got"] - r["ref"]) / abs(r["ref"]))[:8]
 summary = {
@@ -79,6 +90,25 @@ summary = {
     "fraction_within_1e-9": float(np.mean(rel <= 1e-9)), "fraction_within_1e-10": float(np.mean(rel <= 1e-10)),
     "fraction_within_test_tolerance_1e-9_x_max(1,cond/1e7)": float(np.mean(rel <= 1e-9 * np.maximum(1.0, conds / 1e7))),
     "rel_err_over_eps_cond_percentiles": {str(p): float(np.percentile(rel / (1.1e-16 * conds), p)) for p in (50, 90, 99, 100)},
+    "rule_of_tests/test_gpu_parity.py": {
+        "flat_1e-9_vs_oracle": int(np.sum(rel <= 1e-9)),
+        "else_within_3x_of_worse_cpu_fp64_from_80bit": int(sum(1 for r, e in zip(fin, rel) if e > 1e-9 and r["gpu_vs_long_double"] <= max(
+            1e-9, 3 * max(r["oracle_vs_long_double"], r["unblocked_f64_vs_long_double"])))),
+        "failing": [dict(n=r["n"], chunksize=r["chunksize"], cluster=r["cluster"], exact=r["exact"], cond=r["cond"], rel_err=float(e),
+                         gpu_vs_long_double=r["gpu_vs_long_double"], oracle_vs_long_double=r["oracle_vs_long_double"],
+                         unblocked_f64_vs_long_double=r["unblocked_f64_vs_long_double"])
+                    for r, e in zip(fin, rel) if e > 1e-9 and not r["gpu_vs_long_double"] <= max(
+                        1e-9, 3 * max(r["oracle_vs_long_double"], r["unblocked_f64_vs_long_double"]))]},
+    "by_condition_number": {
+        "cond<=1e8": {"evaluations": int(np.sum(conds <= 1e8)),
+                      "max_rel_err": float(np.max(rel[conds <= 1e8])), "fraction_within_1e-9": float(np.mean(rel[conds <= 1e8] <= 1e-9)),
+                      "max_err_over_max(|lnlike|,terms)": float(np.max(rel_sc[conds <= 1e8])),
+                      "fraction_within_1e-9_of_max(|lnlike|,terms)": float(np.mean(rel_sc[conds <= 1e8] <= 1e-9))},
+        "cond>1e8 (differing by more than 1e-10)": {
+            "evaluations": len(tail),
+            "gpu_distance_over_worse_of_two_cpu_fp64_distances_percentiles":
+                {str(p): float(np.percentile(tail_ratio, p)) for p in (50, 90, 100)} if len(tail) else None,
+            "fraction_within_3x": float(np.mean(tail_ratio <= 3.0)) if len(tail) else None}},
     "well_conditioned_subset(cond<=1e7)": {"evaluations": int(np.sum(conds <= 1e7)),
                                           "max_rel_err": float(np.max(rel[conds <= 1e7])) if np.any(conds <= 1e7) else None,
                                           "fraction_within_1e-9": float(np.mean(rel[conds <= 1e7] <= 1e-9)) if np.any(conds <= 1e7) else None},
@@ -96,5 +126,5 @@ summary = {
                    oracle_vs_long_double=r.get("oracle_vs_long_double")) for r in worst],
 }
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(summary, open("gpurun_out/parity_campaign.json", "w"), indent=1)
+json.dump(summary, open("gpurun_out/parity_campaign_seed%d.json" % seed, "w"), indent=1)
 print(json.dumps(summary, indent=1))
