@@ -76,8 +76,18 @@ def _cpu_eval(args):
     return o.lnlike_function(th, t, y, yerr)
 
 
-def cpu_pool_rate(n, evals_per_core, seed=0, steps=1, warmup=0, cores=None):
-    """Oracle evaluations per second with one single-threaded worker process per usable core."""
+def _cpu_eval_hodlr(args):
+    from oracle import hodlr_oracle as h
+
+    th, t, y, yerr = args
+    return h.lnlike_function(th, t, y, yerr)          # george's defaults: nleaf=100, tol=1e-12
+
+
+def cpu_pool_rate(n, evals_per_core, seed=0, steps=1, warmup=0, cores=None, solver="dense"):
+    """Oracle evaluations per second with one single-threaded worker process per usable core.  solver: "dense" (NumPy /
+    LAPACK Cholesky, george's BasicSolver arithmetic) or "hodlr" (restatement of george's HODLRSolver, the solver
+    gprot/model.py:343 selects)."""
+    _cpu_eval = globals()["_cpu_eval_hodlr" if solver == "hodlr" else "_cpu_eval"]
     import multiprocessing as mp
 
     from gprotation_b200.synth import synthetic_lightcurve
@@ -111,20 +121,24 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0))
     epc = 1
     W = max(args.warmup, 3)                                    # the same warm-up count as the CUDA arm
-    rate, cores, nev, times = cpu_pool_rate(N_POINTS, epc, steps=max(1, args.steps), warmup=W, cores=cores)
+    rate, cores, nev, times = cpu_pool_rate(N_POINTS, epc, steps=max(1, args.steps), warmup=W, cores=cores, solver="hodlr")
+    dense_rate = cpu_pool_rate(N_POINTS, epc, steps=1, warmup=1, cores=cores, solver="dense")[0]
     ms = 1e3 * sum(times) / len(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: 1 star, N=2048; each step = %d proposals (one per host core), bounded sample of the "
-                               "1024-proposal launch" % nev, "n": N_POINTS, "batch": nev},
+                               "1024-proposal launch; CPU arm: a rate over %d timed steps after %d warm-up steps" % (nev, len(times), W),
+                   "n": N_POINTS, "batch": nev},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d evals per step (1 per core), dense NumPy/LAPACK restatement of george's matrix, "
-                                   "1 BLAS thread per process" % nev,
-                         "note": "dense O(N^3) port; the reference itself runs george's HODLR solver (O(N log^2 N), approximate, "
-                                 "tol 1e-12), not installable offline -- the paper quotes ~100 ms per evaluation per core at N~1300 "
-                                 "(documents/ms.tex:533-537); see cpu_baseline.hodlr in the CUDA arm's line for a timed HODLR restatement"},
+                         "sample": "%d evals per step (1 per core); restatement of the solver the reference uses -- george "
+                                   "HODLRSolver (nleaf=100, tol=1e-12; gprot/model.py:343), oracle/hodlr_oracle.py in NumPy, 1 BLAS "
+                                   "thread per process" % nev,
+                         "dense_lapack_evals_per_s": dense_rate,
+                         "note": "george itself (C++/Eigen HODLR) is not installable offline; the paper quotes ~100 ms per evaluation "
+                                 "per core at N~1300 on a 2015 laptop (documents/ms.tex:533-537).  The dense NumPy/LAPACK port of the "
+                                 "same matrix (george BasicSolver arithmetic) is timed beside it"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -572,7 +586,12 @@ def cpu_baseline_worker():
     single_ms = 1e3 * sum(times) / len(times) / 2
     # BASELINE configs[0] beside it: N=1000, 32 walkers on the same pool
     c1_rate, _, c1_nev, _ = cpu_pool_rate(1000, max(1, 32 // cores), steps=2, warmup=1, cores=min(cores, 32))
+    h_rate, _, h_nev, h_times = cpu_pool_rate(N_POINTS, 2, steps=2, warmup=1, cores=cores, solver="hodlr")
     print(json.dumps({"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "c1_n1000_evals_per_s": c1_rate,
+                      "hodlr": {"value": h_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d evals per pass, 2 timed passes, N=2048: NumPy restatement of george's HODLRSolver (nleaf=100, "
+                                          "tol=1e-12), the O(N log^2 N) solver the reference actually runs (gprot/model.py:343); "
+                                          "%.0f ms per evaluation per core" % (h_nev, 1e3 * sum(h_times) / len(h_times) / 2)},
                       "sample": "%d evals per pass (2 per core), 2 timed passes, N=2048, same synthetic star generator; "
                                 "one single-threaded NumPy/LAPACK process per core (the reference's --ncores MultiPool layout); "
                                 "%.0f ms per evaluation per core" % (nev, single_ms)}))

@@ -25,6 +25,8 @@ SIGNATURES = {
     "gprot_last_error": (c_char_p, [c_void_p]),
     "gprot_register_lc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
     "gprot_unregister_all": (c_int, [c_void_p]),
+    "gprot_unregister_lc": (c_int, [c_void_p, c_int]),
+    "gprot_generation": (c_int64, [c_void_p]),
     "gprot_lnlike_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_uint, c_void_p]),
     "gprot_lnprior_batch": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_int, c_void_p]),
     "gprot_lnpost_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
@@ -39,6 +41,9 @@ SIGNATURES = {
     "gprot_group_register_lc": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
     "gprot_group_unregister_all": (c_int, [c_void_p]),
     "gprot_group_lnlike_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_uint]),
+    "gprot_group_unregister_lc": (c_int, [c_void_p, c_int]),
+    "gprot_group_lnpost_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
+                                         c_void_p, c_int, c_void_p, c_void_p, c_uint]),
     "gprot_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "gprot_launch_count": (c_int64, [c_void_p]),
     "gprot_measure_dmma_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),

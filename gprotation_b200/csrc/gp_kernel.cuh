@@ -886,6 +886,9 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         const double mingap2 = prm.chunk_mingap2[chunk];
         if (!hyper_ok(h, mingap2)) {
             if (tid == 0 && crank == 0) prm.prob_out[prob] = -INFINITY;
+            // every CTA of the cluster takes this branch (same theta, same chunk): meet before rank 0 pops the next problem
+            // and overwrites the peers' sm.prob, which their slower threads may not have read yet
+            if (CL > 1) cluster_sync();
             continue;
         }
         const bool white_off = mingap2 < h.thr;

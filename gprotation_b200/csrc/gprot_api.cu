@@ -25,6 +25,9 @@ extern template __global__ void gp_lnlike64_kernel<true>(const Params);
 #include <cstring>
 #include <limits>
 #include <new>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,8 +35,56 @@ extern template __global__ void gp_lnlike64_kernel<true>(const Params);
 using namespace gprot;
 
 struct gprot_ctx;
+
+// one persistent host thread per device of a group: gprot_group_* calls hand it a closure and wait (no thread is
+// created or joined per call)
+struct group_worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = false, quit = false;
+    int rc = 0;
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            std::function<int()> f = std::move(job);
+            has_job = false;
+            lk.unlock();
+            const int r = f();
+            lk.lock();
+            rc = r;
+            done = true;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<int()> f) {
+        std::lock_guard<std::mutex> lk(mu);
+        job = std::move(f);
+        has_job = true;
+        done = false;
+        cv.notify_all();
+    }
+    int wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done; });
+        return rc;
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+            cv.notify_all();
+        }
+        if (th.joinable()) th.join();
+    }
+};
+
 struct gprot_group {
     std::vector<gprot_ctx*> ctxs;
+    std::vector<group_worker*> workers;
     std::string err;
 };
 
@@ -46,12 +97,18 @@ struct gprot_ctx {
     std::vector<long long> h_chunk_off;
     std::vector<int> h_chunk_n;
     std::vector<double> h_chunk_mingap2;
-    std::vector<int> lc_first_chunk, lc_nchunks;
-    bool arena_dirty = true;
-    // device copies
+    std::vector<int> lc_first_chunk, lc_nchunks;        // lc_nchunks[id] == 0: unregistered (ids are never reused until unregister_all)
+    size_t dead_points = 0;                             // arena points that belong to unregistered light curves
+    int64_t generation = 0;                             // bumped whenever previously returned ids stop being valid
+    // device copies: grown geometrically, only the new tail is uploaded after a registration
     double *d_t = nullptr, *d_y = nullptr, *d_yerr = nullptr, *d_chunk_mingap2 = nullptr;
     long long* d_chunk_off = nullptr;
     int* d_chunk_n = nullptr;
+    size_t cap_points = 0, up_points = 0, cap_chunks = 0, up_chunks = 0;
+    // pinned host staging for the problem list of a call (reused; ev_stage marks the end of its last upload)
+    int* h_stage = nullptr; size_t cap_stage = 0;
+    cudaEvent_t ev_stage = nullptr; bool stage_pending = false;
+    int max_lslots = 0;                                 // > 0: the factor scratch was capped at this many slots by device memory
     // per-call buffers (grown on demand)
     double* d_theta = nullptr; size_t cap_theta = 0;
     double* d_out = nullptr; size_t cap_out = 0;
@@ -65,7 +122,7 @@ struct gprot_ctx {
     double* d_lscratch = nullptr; size_t lslot_stride = 0; int lslots = 0;
     double* d_vscratch = nullptr; int v_npad = 0; int vslots = 0;
     double* d_wg = nullptr; int* d_cctr = nullptr; int cslots = 0;      // cluster kernels: W exchange + row counters
-    // problem-list cache (same B, all rows on one light curve, no mask)
+    // problem-list cache: the device list of the last call without a mask whose rows all use ONE light curve
     long long cache_B = -1; int cache_lc = -1; int cache_nprob = 0; int cache_tmax = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -105,24 +162,76 @@ int grow(gprot_ctx* ctx, T** p, size_t* cap, size_t need) {
     return 0;
 }
 
+// device arena = host arena: grow geometrically (device-to-device copy of what is already there), upload only the tail
+// appended since the last call.  Kernels in flight only read below up_points / up_chunks.
+template <class T>
+int grow_keep(gprot_ctx* ctx, T** p, size_t old_cap, size_t new_cap, size_t used) {
+    T* q = nullptr;
+    CU(ctx, cudaMalloc((void**)&q, std::max<size_t>(new_cap, 2) * sizeof(T)));
+    if (*p && used) CU(ctx, cudaMemcpy(q, *p, used * sizeof(T), cudaMemcpyDeviceToDevice));
+    if (*p) CU(ctx, cudaFree(*p));
+    (void)old_cap;
+    *p = q;
+    return 0;
+}
+
 int upload_arena(gprot_ctx* ctx) {
-    if (!ctx->arena_dirty) return 0;
-    CU(ctx, cudaDeviceSynchronize());
-    auto rea = [&](void** p, const void* src, size_t bytes) -> int {
-        if (*p) CU(ctx, cudaFree(*p));
-        *p = nullptr;
-        CU(ctx, cudaMalloc(p, std::max<size_t>(bytes, 16)));
-        CU(ctx, cudaMemcpy(*p, src, bytes, cudaMemcpyHostToDevice));
-        return 0;
-    };
     const size_t n = ctx->h_t.size(), m = ctx->h_chunk_n.size();
-    if (rea((void**)&ctx->d_t, ctx->h_t.data(), n * 8)) return 1;
-    if (rea((void**)&ctx->d_y, ctx->h_y.data(), n * 8)) return 1;
-    if (rea((void**)&ctx->d_yerr, ctx->h_yerr.data(), n * 8)) return 1;
-    if (rea((void**)&ctx->d_chunk_off, ctx->h_chunk_off.data(), m * 8)) return 1;
-    if (rea((void**)&ctx->d_chunk_n, ctx->h_chunk_n.data(), m * 4)) return 1;
-    if (rea((void**)&ctx->d_chunk_mingap2, ctx->h_chunk_mingap2.data(), m * 8)) return 1;
-    ctx->arena_dirty = false;
+    if (n == ctx->up_points && m == ctx->up_chunks) return 0;
+    if (n > ctx->cap_points) {
+        CU(ctx, cudaDeviceSynchronize());                       // nothing may still read the old buffers when they are freed
+        const size_t c = std::max<size_t>(std::max(n, 2 * ctx->cap_points), 1 << 14);
+        if (grow_keep(ctx, &ctx->d_t, ctx->cap_points, c, ctx->up_points) || grow_keep(ctx, &ctx->d_y, ctx->cap_points, c, ctx->up_points) ||
+            grow_keep(ctx, &ctx->d_yerr, ctx->cap_points, c, ctx->up_points)) return 1;
+        ctx->cap_points = c;
+    }
+    if (m > ctx->cap_chunks) {
+        CU(ctx, cudaDeviceSynchronize());
+        const size_t c = std::max<size_t>(std::max(m, 2 * ctx->cap_chunks), 256);
+        if (grow_keep(ctx, &ctx->d_chunk_off, ctx->cap_chunks, c, ctx->up_chunks) || grow_keep(ctx, &ctx->d_chunk_n, ctx->cap_chunks, c, ctx->up_chunks) ||
+            grow_keep(ctx, &ctx->d_chunk_mingap2, ctx->cap_chunks, c, ctx->up_chunks)) return 1;
+        ctx->cap_chunks = c;
+    }
+    const size_t p0 = ctx->up_points, c0 = ctx->up_chunks;
+    if (n > p0) {
+        CU(ctx, cudaMemcpy(ctx->d_t + p0, ctx->h_t.data() + p0, (n - p0) * 8, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->d_y + p0, ctx->h_y.data() + p0, (n - p0) * 8, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->d_yerr + p0, ctx->h_yerr.data() + p0, (n - p0) * 8, cudaMemcpyHostToDevice));
+    }
+    if (m > c0) {
+        CU(ctx, cudaMemcpy(ctx->d_chunk_off + c0, ctx->h_chunk_off.data() + c0, (m - c0) * 8, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->d_chunk_n + c0, ctx->h_chunk_n.data() + c0, (m - c0) * 4, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->d_chunk_mingap2 + c0, ctx->h_chunk_mingap2.data() + c0, (m - c0) * 8, cudaMemcpyHostToDevice));
+    }
+    ctx->up_points = n;
+    ctx->up_chunks = m;
+    return 0;
+}
+
+// drop the arena points of unregistered light curves once they outweigh the live ones: ids keep their meaning, the
+// chunk tables are rewritten and everything is uploaded again (rare: amortised over the registrations that caused it)
+int compact_arena(gprot_ctx* ctx) {
+    CU(ctx, cudaDeviceSynchronize());
+    std::vector<double> t, y, e, g2;
+    std::vector<long long> off;
+    std::vector<int> cn;
+    for (size_t id = 0; id < ctx->lc_first_chunk.size(); id++) {
+        const int f = ctx->lc_first_chunk[id], m = ctx->lc_nchunks[id];
+        if (m == 0) continue;
+        ctx->lc_first_chunk[id] = (int)cn.size();
+        for (int c = f; c < f + m; c++) {
+            const size_t o0 = (size_t)ctx->h_chunk_off[c], len = (size_t)ctx->h_chunk_n[c] + ((size_t)ctx->h_chunk_n[c] & 1);
+            off.push_back((long long)t.size());
+            cn.push_back(ctx->h_chunk_n[c]);
+            g2.push_back(ctx->h_chunk_mingap2[c]);
+            t.insert(t.end(), ctx->h_t.begin() + o0, ctx->h_t.begin() + o0 + len);
+            y.insert(y.end(), ctx->h_y.begin() + o0, ctx->h_y.begin() + o0 + len);
+            e.insert(e.end(), ctx->h_yerr.begin() + o0, ctx->h_yerr.begin() + o0 + len);
+        }
+    }
+    ctx->h_t.swap(t); ctx->h_y.swap(y); ctx->h_yerr.swap(e);
+    ctx->h_chunk_off.swap(off); ctx->h_chunk_n.swap(cn); ctx->h_chunk_mingap2.swap(g2);
+    ctx->up_points = 0; ctx->up_chunks = 0; ctx->dead_points = 0;
     ctx->cache_B = -1;
     return 0;
 }
@@ -219,84 +328,110 @@ int choose_cluster(gprot_ctx* ctx, int nprob, int tmax) {
     return best;
 }
 
-// (theta row, chunk) problems of a launch, their per-row ranges for the chunk sum, and the queue order; uploaded to the
-// device unless the cached list of the previous identical call (same B, every row on light curve 0, no mask) is valid
+// (theta row, chunk) problems of a launch, their per-row ranges for the chunk sum, and the queue order.  The list lives on
+// the device; it is rebuilt only when the call differs from the cached one (same B, every row on the same light curve,
+// no mask -- what a sampler step or a bench loop repeats).  A rebuild fills pinned host staging owned by the context
+// and uploads it asynchronously on the caller's stream: no stream synchronisation, no pageable copies.
 struct ProblemList { int nprob = 0, tmax = 0, nmax = 0; };
 
 int build_problem_list(gprot_ctx* ctx, int64_t B, const int32_t* lc_id, const unsigned char* mask, cudaStream_t st, ProblemList& pl) {
     int& nprob = pl.nprob; int& tmax = pl.tmax; int& nmax = pl.nmax;
-    const bool cacheable = (lc_id == nullptr && mask == nullptr);
-    if (cacheable && ctx->cache_B == B && ctx->cache_lc == 0) {
+    const int nlc = (int)ctx->lc_first_chunk.size();
+    int uniform = lc_id ? lc_id[0] : 0;                      // every row on one light curve?
+    if (lc_id)
+        for (int64_t b = 1; b < B && uniform >= 0; b++)
+            if (lc_id[b] != uniform) uniform = -1;
+    const bool cacheable = (uniform >= 0 && mask == nullptr);
+    if (cacheable && ctx->cache_B == B && ctx->cache_lc == uniform) {
         nprob = ctx->cache_nprob;
         tmax = ctx->cache_tmax;
         nmax = ctx->last_nmax;
-    } else {
-        std::vector<int> ptheta, pchunk, rfirst((size_t)B), rcount((size_t)B);
-        const int nlc = (int)ctx->lc_first_chunk.size();
-        for (int64_t b = 0; b < B; b++) {
-            const int lc = lc_id ? lc_id[b] : 0;
-            if (lc < 0 || lc >= nlc) return fail(ctx, "lc_id out of range");
-            rfirst[b] = (int)ptheta.size();
-            if (mask && !mask[b]) { rcount[b] = 0; continue; }
-            const int f = ctx->lc_first_chunk[lc], m = ctx->lc_nchunks[lc];
-            rcount[b] = m;
-            for (int c = 0; c < m; c++) {
-                ptheta.push_back((int)b);
-                pchunk.push_back(f + c);
-                tmax = std::max(tmax, (ctx->h_chunk_n[f + c] + BS - 1) / BS);
-                nmax = std::max(nmax, ctx->h_chunk_n[f + c]);
-            }
+        return 0;
+    }
+    // ---- size of the list
+    size_t np = 0;
+    for (int64_t b = 0; b < B; b++) {
+        const int lc = lc_id ? lc_id[b] : 0;
+        if (lc < 0 || lc >= nlc) return fail(ctx, "lc_id out of range");
+        if (ctx->lc_nchunks[lc] == 0) return fail(ctx, "lc_id refers to an unregistered light curve");
+        if (!mask || mask[b]) np += (size_t)ctx->lc_nchunks[lc];
+    }
+    if (np > (size_t)std::numeric_limits<int>::max()) return fail(ctx, "too many (row, chunk) problems in one call");
+    // ---- pinned staging: [row_first B][row_count B][prob_theta np][prob_chunk np][order np]
+    const size_t need = 2 * (size_t)B + 3 * np;
+    if (ctx->stage_pending) {                                  // the previous list may still be on its way to the device
+        CU(ctx, cudaEventSynchronize(ctx->ev_stage));
+        ctx->stage_pending = false;
+    }
+    if (need > ctx->cap_stage) {
+        if (ctx->h_stage) CU(ctx, cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr;
+        const size_t c = std::max(need, 2 * ctx->cap_stage);
+        CU(ctx, cudaMallocHost((void**)&ctx->h_stage, c * sizeof(int)));
+        ctx->cap_stage = c;
+    }
+    int* rfirst = ctx->h_stage; int* rcount = rfirst + B; int* ptheta = rcount + B; int* pchunk = ptheta + np; int* order = pchunk + np;
+    int k = 0, nmin = std::numeric_limits<int>::max();
+    for (int64_t b = 0; b < B; b++) {
+        const int lc = lc_id ? lc_id[b] : 0;
+        rfirst[b] = k;
+        if (mask && !mask[b]) { rcount[b] = 0; continue; }
+        const int f = ctx->lc_first_chunk[lc], m = ctx->lc_nchunks[lc];
+        rcount[b] = m;
+        for (int c = 0; c < m; c++, k++) {
+            ptheta[k] = (int)b;
+            pchunk[k] = f + c;
+            const int v = ctx->h_chunk_n[f + c];
+            nmax = std::max(nmax, v);
+            nmin = std::min(nmin, v);
         }
-        nprob = (int)ptheta.size();
-        if ((size_t)B > ctx->cap_rows) {
-            if (ctx->d_row_first) cudaFree(ctx->d_row_first);
-            if (ctx->d_row_count) cudaFree(ctx->d_row_count);
-            ctx->d_row_first = ctx->d_row_count = nullptr;
-            const size_t c = std::max<size_t>((size_t)B, ctx->cap_rows * 2);
-            CU(ctx, cudaMalloc((void**)&ctx->d_row_first, c * 4));
-            CU(ctx, cudaMalloc((void**)&ctx->d_row_count, c * 4));
-            ctx->cap_rows = c;
-        }
-        if ((size_t)nprob > ctx->cap_prob) {
-            if (ctx->d_prob_theta) cudaFree(ctx->d_prob_theta);
-            if (ctx->d_prob_chunk) cudaFree(ctx->d_prob_chunk);
-            if (ctx->d_prob_out) cudaFree(ctx->d_prob_out);
-            if (ctx->d_prob_order) cudaFree(ctx->d_prob_order);
-            ctx->d_prob_theta = ctx->d_prob_chunk = ctx->d_prob_order = nullptr; ctx->d_prob_out = nullptr;
-            const size_t c = std::max<size_t>(nprob, ctx->cap_prob * 2);
-            CU(ctx, cudaMalloc((void**)&ctx->d_prob_theta, c * 4));
-            CU(ctx, cudaMalloc((void**)&ctx->d_prob_chunk, c * 4));
-            CU(ctx, cudaMalloc((void**)&ctx->d_prob_out, c * 8));
-            CU(ctx, cudaMalloc((void**)&ctx->d_prob_order, c * 4));
-            ctx->cap_prob = c;
-        }
-        CU(ctx, cudaMemcpyAsync(ctx->d_row_first, rfirst.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-        CU(ctx, cudaMemcpyAsync(ctx->d_row_count, rcount.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
-        if (nprob > 0) {
-            CU(ctx, cudaMemcpyAsync(ctx->d_prob_theta, ptheta.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
-            CU(ctx, cudaMemcpyAsync(ctx->d_prob_chunk, pchunk.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
-        }
+    }
+    nprob = k;
+    tmax = (nmax + BS - 1) / BS;
+    if ((size_t)B > ctx->cap_rows) {
+        CU(ctx, cudaStreamSynchronize(st));                     // a queued launch may still read the old arrays
+        if (ctx->d_row_first) CU(ctx, cudaFree(ctx->d_row_first));
+        if (ctx->d_row_count) CU(ctx, cudaFree(ctx->d_row_count));
+        ctx->d_row_first = ctx->d_row_count = nullptr;
+        const size_t c = std::max<size_t>((size_t)B, ctx->cap_rows * 2);
+        CU(ctx, cudaMalloc((void**)&ctx->d_row_first, c * 4));
+        CU(ctx, cudaMalloc((void**)&ctx->d_row_count, c * 4));
+        ctx->cap_rows = c;
+    }
+    if ((size_t)nprob > ctx->cap_prob) {
+        CU(ctx, cudaStreamSynchronize(st));
+        if (ctx->d_prob_theta) CU(ctx, cudaFree(ctx->d_prob_theta));
+        if (ctx->d_prob_chunk) CU(ctx, cudaFree(ctx->d_prob_chunk));
+        if (ctx->d_prob_out) CU(ctx, cudaFree(ctx->d_prob_out));
+        if (ctx->d_prob_order) CU(ctx, cudaFree(ctx->d_prob_order));
+        ctx->d_prob_theta = ctx->d_prob_chunk = ctx->d_prob_order = nullptr; ctx->d_prob_out = nullptr;
+        const size_t c = std::max<size_t>(nprob, ctx->cap_prob * 2);
+        CU(ctx, cudaMalloc((void**)&ctx->d_prob_theta, c * 4));
+        CU(ctx, cudaMalloc((void**)&ctx->d_prob_chunk, c * 4));
+        CU(ctx, cudaMalloc((void**)&ctx->d_prob_out, c * 8));
+        CU(ctx, cudaMalloc((void**)&ctx->d_prob_order, c * 4));
+        ctx->cap_prob = c;
+    }
+    CU(ctx, cudaMemcpyAsync(ctx->d_row_first, rfirst, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ctx->d_row_count, rcount, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    ctx->use_order = false;
+    if (nprob > 0) {
+        CU(ctx, cudaMemcpyAsync(ctx->d_prob_theta, ptheta, (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
+        CU(ctx, cudaMemcpyAsync(ctx->d_prob_chunk, pchunk, (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
         // Mixed problem sizes: the persistent CTAs take the largest problems first (longest-processing-time-first), so
         // that a big problem is never the last one popped.  Outputs keep their listed positions.
-        std::vector<int> order;
-        ctx->use_order = false;
-        if (nprob > 1) {
-            int nmin = ctx->h_chunk_n[pchunk[0]], nmax = nmin;
-            for (int k = 1; k < nprob; k++) { const int v = ctx->h_chunk_n[pchunk[k]]; nmin = std::min(nmin, v); nmax = std::max(nmax, v); }
-            if ((nmax + BS - 1) / BS != (nmin + BS - 1) / BS) {
-                order.resize((size_t)nprob);
-                for (int k = 0; k < nprob; k++) order[k] = k;
-                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->h_chunk_n[pchunk[a]] > ctx->h_chunk_n[pchunk[b]]; });
-                CU(ctx, cudaMemcpyAsync(ctx->d_prob_order, order.data(), (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
-                ctx->use_order = true;
-            }
+        if (nprob > 1 && (nmax + BS - 1) / BS != (nmin + BS - 1) / BS) {
+            for (int i = 0; i < nprob; i++) order[i] = i;
+            std::stable_sort(order, order + nprob, [&](int a, int b) { return ctx->h_chunk_n[pchunk[a]] > ctx->h_chunk_n[pchunk[b]]; });
+            CU(ctx, cudaMemcpyAsync(ctx->d_prob_order, order, (size_t)nprob * 4, cudaMemcpyHostToDevice, st));
+            ctx->use_order = true;
         }
-        CU(ctx, cudaStreamSynchronize(st));   // the host vectors go out of scope
-        ctx->last_nmax = nmax;
-        if (cacheable) { ctx->cache_B = B; ctx->cache_lc = 0; ctx->cache_nprob = nprob; ctx->cache_tmax = tmax; }
-        else ctx->cache_B = -1;
     }
-
+    CU(ctx, cudaEventRecord(ctx->ev_stage, st));
+    ctx->stage_pending = true;
+    ctx->last_nmax = nmax;
+    if (cacheable) { ctx->cache_B = B; ctx->cache_lc = uniform; ctx->cache_nprob = nprob; ctx->cache_tmax = tmax; }
+    else ctx->cache_B = -1;
     return 0;
 }
 
@@ -348,7 +483,9 @@ constexpr size_t WG_STRIDE = 2 * (size_t)(W_DOUBLES + BS) + 2 * TCAP;
 // factor scratch, per-point vectors and (cluster kernels) the W exchange buffers, grown on demand; may lower lp.slots to
 // what fits in device memory
 int ensure_scratch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
-    if (lp.stride > ctx->lslot_stride || lp.slots > ctx->lslots) {
+    // a previous call found that device memory holds only max_lslots slots of this stride: do not try again
+    const bool capped = ctx->max_lslots > 0 && lp.stride <= ctx->lslot_stride && ctx->lslots >= ctx->max_lslots;
+    if (!capped && (lp.stride > ctx->lslot_stride || lp.slots > ctx->lslots)) {
         CU(ctx, cudaDeviceSynchronize());
         if (ctx->d_lscratch) CU(ctx, cudaFree(ctx->d_lscratch));
         ctx->d_lscratch = nullptr;
@@ -356,9 +493,15 @@ int ensure_scratch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
         int want = std::max(lp.slots, ctx->lslots);
         size_t freeb = 0, totalb = 0;
         CU(ctx, cudaMemGetInfo(&freeb, &totalb));
+        // per slot: the factor scratch, the per-point vectors and (cluster kernels) the W exchange buffers allocated below
+        const size_t per_slot = s2 * 8 + (size_t)5 * std::max(lp.npad, ctx->v_npad) * 8 + WG_STRIDE * 8 + (TCAP + 2) * 4;
         const size_t budget = (size_t)(0.85 * (double)freeb);
-        while (want > 1 && (size_t)want * s2 * 8 > budget) want--;
-        if ((size_t)want * s2 * 8 > budget) return fail(ctx, "not enough device memory for one factor scratch slot");
+        ctx->max_lslots = 0;
+        if ((size_t)want * per_slot > budget) {
+            want = (int)(budget / per_slot);
+            ctx->max_lslots = want;
+        }
+        if (want < 1) return fail(ctx, "not enough device memory for one factor scratch slot");
         CU(ctx, cudaMalloc((void**)&ctx->d_lscratch, (size_t)want * s2 * 8));
         ctx->lslot_stride = s2;
         ctx->lslots = want;
@@ -473,7 +616,7 @@ int lnlike_core(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* l
 
 extern "C" {
 
-int gprot_abi_version(void) { return 1; }
+int gprot_abi_version(void) { return 2; }
 
 const char* gprot_last_error(const gprot_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
@@ -499,7 +642,7 @@ int gprot_create(int device, gprot_ctx** out) {
     }
     ctx->num_sms = p.multiProcessorCount;
     if (cudaMalloc((void**)&ctx->d_counter, 64) != cudaSuccess || cudaMalloc((void**)&ctx->d_timing, 16 * 8) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, "context allocation failed");
     }
@@ -518,6 +661,8 @@ int gprot_destroy(gprot_ctx* ctx) {
         if (p) cudaFree(p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     delete ctx;
     return 0;
 }
@@ -554,20 +699,37 @@ int gprot_register_lc(gprot_ctx* ctx, int m, const int* n, const double* t, cons
     }
     ctx->lc_first_chunk.push_back(first);
     ctx->lc_nchunks.push_back(m);
-    ctx->arena_dirty = true;
     if (lc_id) *lc_id = (int)ctx->lc_first_chunk.size() - 1;
+    return 0;                                                // the new tail of the arena goes to the device with the next call
+}
+
+int gprot_unregister_lc(gprot_ctx* ctx, int lc_id) {
+    if (!ctx) return fail(nullptr, "null context");
+    if (lc_id < 0 || lc_id >= (int)ctx->lc_first_chunk.size() || ctx->lc_nchunks[lc_id] == 0) return fail(ctx, "lc_id is not a registered light curve");
+    const int f = ctx->lc_first_chunk[lc_id], m = ctx->lc_nchunks[lc_id];
+    size_t live = 0;
+    for (int c = f; c < f + m; c++) ctx->dead_points += (size_t)ctx->h_chunk_n[c] + ((size_t)ctx->h_chunk_n[c] & 1);
+    ctx->lc_nchunks[lc_id] = 0;
+    if (ctx->cache_lc == lc_id) ctx->cache_B = -1;
+    live = ctx->h_t.size() - ctx->dead_points;
+    if (ctx->dead_points > live && ctx->dead_points > (size_t)1 << 16) return compact_arena(ctx);
     return 0;
 }
 
 int gprot_unregister_all(gprot_ctx* ctx) {
     if (!ctx) return fail(nullptr, "null context");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaDeviceSynchronize());                        // a queued launch may still read the arena that is about to be rewritten
     ctx->h_t.clear(); ctx->h_y.clear(); ctx->h_yerr.clear();
     ctx->h_chunk_off.clear(); ctx->h_chunk_n.clear(); ctx->h_chunk_mingap2.clear();
     ctx->lc_first_chunk.clear(); ctx->lc_nchunks.clear();
-    ctx->arena_dirty = true;
+    ctx->up_points = 0; ctx->up_chunks = 0; ctx->dead_points = 0;
     ctx->cache_B = -1;
+    ctx->generation++;                                       // ids handed out before this call are void
     return 0;
 }
+
+int64_t gprot_generation(const gprot_ctx* ctx) { return ctx ? ctx->generation : -1; }
 
 int gprot_lnlike_batch(gprot_ctx* ctx, int64_t B, const double* theta, const int32_t* lc_id, double* out, unsigned flags,
                        void* stream) {
@@ -680,12 +842,18 @@ int gprot_group_create(int ndev, const int* devices, gprot_group** out) {
         }
         g->ctxs.push_back(c);
     }
+    for (size_t i = 0; i < g->ctxs.size(); i++) {
+        group_worker* w = new group_worker;
+        w->th = std::thread([w] { w->loop(); });
+        g->workers.push_back(w);
+    }
     *out = g;
     return 0;
 }
 
 int gprot_group_destroy(gprot_group* g) {
     if (!g) return 0;
+    for (group_worker* w : g->workers) { w->stop(); delete w; }
     for (gprot_ctx* c : g->ctxs) gprot_destroy(c);
     delete g;
     return 0;
@@ -710,7 +878,36 @@ int gprot_group_register_lc(gprot_group* g, int m, const int* n, const double* t
 
 int gprot_group_unregister_all(gprot_group* g) {
     if (!g) return fail(nullptr, "null group");
-    for (gprot_ctx* c : g->ctxs) gprot_unregister_all(c);
+    for (gprot_ctx* c : g->ctxs)
+        if (gprot_unregister_all(c)) return gfail(g, c->err);
+    return 0;
+}
+
+int gprot_group_unregister_lc(gprot_group* g, int lc_id) {
+    if (!g) return fail(nullptr, "null group");
+    for (gprot_ctx* c : g->ctxs)
+        if (gprot_unregister_lc(c, lc_id)) return gfail(g, c->err);
+    return 0;
+}
+
+// rows [lo, lo + cnt) of the batch go to device r; the persistent workers run the devices concurrently
+static int group_run(gprot_group* g, int64_t B, const double* theta, const int32_t* lc_id, const unsigned char* mask, double* out, unsigned flags) {
+    const int64_t G = (int64_t)g->ctxs.size();
+    const int64_t base = B / G, rem = B % G;
+    std::vector<char> used((size_t)G, 0);
+    for (int64_t r = 0; r < G; r++) {
+        const int64_t lo = r * base + std::min<int64_t>(r, rem), cnt = base + (r < rem ? 1 : 0);
+        if (cnt == 0) continue;
+        gprot_ctx* c = g->ctxs[(size_t)r];
+        used[(size_t)r] = 1;
+        g->workers[(size_t)r]->submit([=]() {
+            return lnlike_core(c, cnt, theta + 5 * lo, lc_id ? lc_id + lo : nullptr, mask ? mask + lo : nullptr, out + lo, flags, nullptr);
+        });
+    }
+    int bad = -1;
+    for (int64_t r = 0; r < G; r++)
+        if (used[(size_t)r] && g->workers[(size_t)r]->wait() != 0 && bad < 0) bad = (int)r;
+    if (bad >= 0) return gfail(g, "device " + std::to_string(g->ctxs[(size_t)bad]->device) + ": " + g->ctxs[(size_t)bad]->err);
     return 0;
 }
 
@@ -718,22 +915,21 @@ int gprot_group_lnlike_batch(gprot_group* g, int64_t B, const double* theta, con
     if (!g) return fail(nullptr, "null group");
     if (flags & (GPROT_THETA_ON_DEVICE | GPROT_OUT_ON_DEVICE)) return gfail(g, "gprot_group_lnlike_batch takes host buffers");
     if (B < 0 || (B > 0 && (!theta || !out))) return gfail(g, "bad arguments");
-    const int64_t G = (int64_t)g->ctxs.size();
-    const int64_t base = B / G, rem = B % G;
-    std::vector<int> rc((size_t)G, 0);
-    std::vector<std::thread> th;
-    for (int64_t r = 0; r < G; r++) {
-        const int64_t lo = r * base + std::min<int64_t>(r, rem), cnt = base + (r < rem ? 1 : 0);
-        if (cnt == 0) continue;
-        gprot_ctx* c = g->ctxs[(size_t)r];
-        th.emplace_back([=, &rc]() {
-            rc[(size_t)r] = lnlike_core(c, cnt, theta + 5 * lo, lc_id ? lc_id + lo : nullptr, nullptr, out + lo, flags, nullptr);
-        });
-    }
-    for (std::thread& t : th) t.join();
-    for (int64_t r = 0; r < G; r++)
-        if (rc[(size_t)r]) return gfail(g, "device " + std::to_string(g->ctxs[(size_t)r]->device) + ": " + g->ctxs[(size_t)r]->err);
-    return 0;
+    if (B == 0) return 0;
+    return group_run(g, B, theta, lc_id, nullptr, out, flags);
+}
+
+int gprot_group_lnpost_batch(gprot_group* g, int64_t B, const double* theta, const int32_t* lc_id, const double* bounds,
+                             const double* mu, const double* sigma, double pmin, double pmax, const double* mixture, int k,
+                             double* out_lnprior, double* out_lnlike, unsigned flags) {
+    if (!g) return fail(nullptr, "null group");
+    if (flags & (GPROT_THETA_ON_DEVICE | GPROT_OUT_ON_DEVICE)) return gfail(g, "gprot_group_lnpost_batch takes host buffers");
+    if (B < 0 || (B > 0 && (!theta || !out_lnprior || !out_lnlike))) return gfail(g, "bad arguments");
+    if (B == 0) return 0;
+    if (gprot_lnprior_batch(B, theta, bounds, mu, sigma, pmin, pmax, mixture, k, out_lnprior)) return gfail(g, g_err);
+    std::vector<unsigned char> mask((size_t)B);
+    for (int64_t b = 0; b < B; b++) mask[(size_t)b] = std::isfinite(out_lnprior[b]) ? 1 : 0;
+    return group_run(g, B, theta, lc_id, mask.data(), out_lnlike, flags);
 }
 
 int gprot_debug_read_timing(gprot_ctx* ctx, long long* host_out16) {

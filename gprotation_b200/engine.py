@@ -81,7 +81,16 @@ class GPEngine(object):
         return lc_id.value
 
     def unregister_all(self):
+        """Forget every light curve; ids restart at 0 and `generation` moves on, which voids the ids models cached."""
         self._check(self._lib.gprot_unregister_all(self._ctx))
+
+    def unregister_lc(self, lc_id):
+        """Forget one light curve (its id is not reused)."""
+        self._check(self._lib.gprot_unregister_lc(self._ctx, int(lc_id)))
+
+    @property
+    def generation(self):
+        return int(self._lib.gprot_generation(self._ctx))
 
     # -- evaluation (host buffers)
     def lnlike_batch(self, theta, lc_id=None, exact=False):
@@ -177,6 +186,7 @@ class GPGroup(object):
         if rc != 0:
             raise GProtError(self._lib.gprot_group_last_error(None).decode())
         self.devices = [int(d) for d in dev]
+        self._generation = 0
 
     def close(self):
         if getattr(self, "_grp", None) is not None and self._grp.value:
@@ -213,6 +223,14 @@ class GPGroup(object):
 
     def unregister_all(self):
         self._check(self._lib.gprot_group_unregister_all(self._grp))
+        self._generation += 1
+
+    def unregister_lc(self, lc_id):
+        self._check(self._lib.gprot_group_unregister_lc(self._grp, int(lc_id)))
+
+    @property
+    def generation(self):
+        return self._generation
 
     def lnlike_batch(self, theta, lc_id=None, exact=False):
         theta = _f64(theta).reshape(-1, 5)
@@ -222,3 +240,18 @@ class GPGroup(object):
         self._check(self._lib.gprot_group_lnlike_batch(self._grp, B, theta.ctypes.data, ids.ctypes.data if ids is not None else None,
                                                        out.ctypes.data, _lib.EXACT_KERNEL if exact else 0))
         return out
+
+    def lnpost_batch(self, theta, bounds, mu, sigma, pmin=-np.inf, pmax=np.inf, mixture=None, lc_id=None, exact=False):
+        """(lnprior[B], lnlike[B]) over the devices of the group; rows outside the prior support are not factorised."""
+        theta = _f64(theta).reshape(-1, 5)
+        B = theta.shape[0]
+        lp = np.empty(B, dtype=np.float64)
+        ll = np.empty(B, dtype=np.float64)
+        b, m, s = _f64(bounds).reshape(10), _f64(mu).reshape(4), _f64(sigma).reshape(4)
+        mix = None if mixture is None or len(mixture) == 0 else _f64(mixture).reshape(-1, 3)
+        ids = GPEngine._ids(lc_id, B)
+        self._check(self._lib.gprot_group_lnpost_batch(
+            self._grp, B, theta.ctypes.data, ids.ctypes.data if ids is not None else None, b.ctypes.data, m.ctypes.data,
+            s.ctypes.data, float(pmin), float(pmax), mix.ctypes.data if mix is not None else None,
+            0 if mix is None else mix.shape[0], lp.ctypes.data, ll.ctypes.data, _lib.EXACT_KERNEL if exact else 0))
+        return lp, ll

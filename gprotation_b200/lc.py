@@ -77,6 +77,7 @@ class LightCurve(object):
 
     def _invalidate(self):
         self._x_list = self._y_list = self._yerr_list = None
+        self.version = getattr(self, "version", 0) + 1      # GPRotModel re-registers the light curve when this moves
 
     # ---- sampling / chunking
     def subsample(self, sub, seed=None):
@@ -181,6 +182,7 @@ class LightCurve(object):
             yl += list(lc.y_list)
             el += list(lc.yerr_list)
         self._x_list, self._y_list, self._yerr_list = xl, yl, el
+        self.version = getattr(self, "version", 0) + 1
 
     @property
     def is_split(self):

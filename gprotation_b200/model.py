@@ -83,6 +83,8 @@ class GPRotModel(object):
         self._lc_id = None
         self._lc_key = None
         self._adhoc = {}
+        self._adhoc_generation = -1
+        self._adhoc_max = 32
         if period_mixture is not None:
             self._period_mixture = np.asarray(period_mixture, dtype=np.float64).reshape(-1, 3)
 
@@ -141,12 +143,36 @@ class GPRotModel(object):
             self._engine = get_engine(self._device)
         return self._engine
 
+    @staticmethod
+    def _digest(*arrays):
+        """Content key of a set of arrays (id() is reused after garbage collection and blind to in-place edits)."""
+        import hashlib
+
+        h = hashlib.blake2b(digest_size=16)
+        for a in arrays:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            h.update(np.int64(a.size).tobytes())
+            h.update(a.tobytes())
+        return h.digest()
+
     def _registered_id(self):
-        """Upload the light curve once (the reference hands x, yerr to george on every call)."""
+        """Upload the light curve once (the reference hands x, yerr to george on every call).  The registration is
+        keyed on the light curve's change counter (or, for foreign objects, its content) and on the engine's generation
+        (engine.unregister_all voids every id)."""
         lc = self.lc
         xl = lc.x_list
-        key = (id(lc.x), len(lc.x), None if xl is None else len(xl))
+        version = getattr(lc, "version", None)
+        if version is not None:
+            # gprotation_b200.lc.LightCurve counts every change of its arrays / chunking; the model holds the object, so
+            # its id cannot be recycled (unlike id(lc.x), which a new array may inherit after garbage collection)
+            ident = (id(lc), version, len(lc.x))
+        else:                                                # a foreign light-curve object: key on the content
+            arrays = (lc.x, lc.y, lc.yerr) if xl is None else tuple(xl) + tuple(lc.y_list) + tuple(lc.yerr_list)
+            ident = self._digest(*arrays)
+        key = (ident, None if xl is None else len(xl), self.engine.generation)
         if self._lc_id is None or key != self._lc_key:
+            if self._lc_id is not None and self._lc_key is not None and self._lc_key[2] == self.engine.generation:
+                self.engine.unregister_lc(self._lc_id)            # the light curve changed: drop the stale copy
             if xl is None:
                 self._lc_id = self.engine.register_lc(lc.x, lc.y, lc.yerr)
             else:
@@ -218,21 +244,30 @@ class GPRotModel(object):
     def gp_kernel(self, theta):
         """The reference returns a george kernel object; here the five linear-space hyper-parameters of
         A * ExpSquaredKernel(l) * ExpSine2Kernel(G, P) + WhiteKernel(sigma) that the device kernel consumes."""
-        A, l, G, sigma, P = (float(np.exp(v)) for v in theta)
+        with np.errstate(over='ignore'):
+            A, l, G, sigma, P = (float(np.exp(v)) for v in theta)
         return {'A': A, 'metric': l, 'gamma': G, 'white': sigma, 'period': P}
 
-    def lnlike_function(self, theta, x, y, yerr):
-        # ad-hoc arrays are registered once per content (a digest, not id(): ids are reused after garbage collection)
-        import hashlib
+    def gp(self, theta, x=None, yerr=None):
+        """gprot/model.py:336-347 returns ``george.GP(kernel, solver=HODLRSolver)`` after ``compute(x, sqrt(sigma + yerr**2))``.
+        Here: a handle with the two george.GP methods the reference calls on it -- ``lnlikelihood(y, quiet=True)``
+        (gprot/model.py:354) and ``predict(y, t)`` (code/koi_demo.py:66) -- evaluated by the CUDA engine."""
+        return GPHandle(self, theta, self.x if x is None else x, self.yerr if yerr is None else yerr)
 
-        h = hashlib.blake2b(digest_size=16)
-        for a in (x, y, yerr):
-            h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
-        key = h.digest()
-        lc_id = self._adhoc.get(key)
+    def lnlike_function(self, theta, x, y, yerr):
+        # ad-hoc arrays are registered once per content and kept in a small LRU (the arena must not grow without bound);
+        # an engine.unregister_all() elsewhere voids the cached ids (generation)
+        if self._adhoc_generation != self.engine.generation:
+            self._adhoc.clear()
+            self._adhoc_generation = self.engine.generation
+        key = self._digest(x, y, yerr)
+        lc_id = self._adhoc.pop(key, None)
         if lc_id is None:
             lc_id = self.engine.register_lc(x, y, yerr)
-            self._adhoc[key] = lc_id
+            while len(self._adhoc) >= self._adhoc_max:
+                old_key = next(iter(self._adhoc))
+                self.engine.unregister_lc(self._adhoc.pop(old_key))
+        self._adhoc[key] = lc_id                                 # most recently used last
         lnl = float(self.engine.lnlike_batch(np.asarray(theta, dtype=np.float64).reshape(1, 5), lc_id=lc_id)[0])
         return lnl if np.isfinite(lnl) else -np.inf
 
@@ -297,9 +332,9 @@ class GPRotModel(object):
             groups = [(np.asarray(lc.x), np.asarray(lc.y), np.asarray(lc.yerr))]
         else:
             groups = [(np.asarray(a), np.asarray(b), np.asarray(c)) for a, b, c in zip(lc.x_list, lc.y_list, lc.yerr_list)]
-        eng = _engine.GPEngine(self._device if device is None else device)      # scratch context: the model's own stays untouched
+        eng = self.engine if device is None else get_engine(device)     # the model's own context; the probes are dropped again
+        ids = []
         try:
-            ids = []
             for ts in t_pred:
                 gap = [max(g[0].min() - ts, ts - g[0].max(), 0.0) for g in groups]
                 x, y, e = groups[int(np.argmin(gap))]
@@ -308,7 +343,8 @@ class GPRotModel(object):
                     ids.append(eng.register_lc(xa, np.append(y, ystar), ea))
             f = eng.lnlike_batch(np.tile(theta, (len(ids), 1)), lc_id=np.asarray(ids, dtype=np.int32)).reshape(-1, 3)
         finally:
-            eng.close()
+            for i in ids:
+                eng.unregister_lc(i)
         curv = (f[:, 2] + f[:, 0] - 2.0 * f[:, 1]) / (s * s)        # = -1 / s*^2
         slope = (f[:, 2] - f[:, 0]) / (2.0 * s)                     # = mu* / s*^2
         with np.errstate(divide='ignore', invalid='ignore'):
@@ -333,6 +369,37 @@ class GPRotModel(object):
 
     def mnest_loglike(self, cube, ndim, nparams):
         return self.lnpost(cube)
+
+
+class GPHandle(object):
+    """The part of the george.GP surface GProtation touches, for one (theta, x, yerr): see ``GPRotModel.gp``."""
+
+    def __init__(self, model, theta, x, yerr):
+        self.model = model
+        self.theta = np.asarray(theta, dtype=np.float64).reshape(5)
+        self.x = np.asarray(x, dtype=np.float64)
+        self.yerr = np.asarray(yerr, dtype=np.float64)
+        self.kernel = model.gp_kernel(self.theta)
+        self.computed = True
+
+    def lnlikelihood(self, y, quiet=False):
+        """george.GP.lnlikelihood: -inf on failure when ``quiet``, else numpy.linalg.LinAlgError (as george raises)."""
+        lnl = self.model.lnlike_function(self.theta, self.x, y, self.yerr)
+        if not np.isfinite(lnl) and not quiet:
+            raise np.linalg.LinAlgError("covariance matrix is not positive definite (or not finite)")
+        return lnl
+
+    def predict(self, y, t, return_var=True):
+        """Predictive mean (and variance) at ``t`` given ``y`` at the handle's x.  george returns the full predictive
+        covariance; the reference only plots mean and standard deviation, so only the diagonal is provided."""
+        from .lc import LightCurve
+
+        probe = GPRotModel(LightCurve(self.x, y, self.yerr, chunksize=None), engine=self.model.engine)
+        try:
+            return probe.predict(self.theta, t, return_var=return_var)
+        finally:
+            if probe._lc_id is not None:
+                probe.engine.unregister_lc(probe._lc_id)
 
 
 class KeplerGPRotModel(GPRotModel):

@@ -51,7 +51,12 @@ const char *gprot_last_error(const gprot_ctx *ctx);
  * every call, gprot/model.py:343-346).  Returns an id through lc_id. */
 int gprot_register_lc(gprot_ctx *ctx, int m, const int *n, const double *t, const double *y,
                       const double *yerr, int *lc_id);
+/* Forget ONE light curve (its id is not reused; the arena space is reclaimed by compaction once dead points outweigh
+ * live ones) or ALL of them (ids restart at 0).  gprot_generation counts the gprot_unregister_all calls so that a caller
+ * that caches ids -- GPRotModel caches the id of its LightCurve -- can tell that they are void. */
+int gprot_unregister_lc(gprot_ctx *ctx, int lc_id);
 int gprot_unregister_all(gprot_ctx *ctx);
+int64_t gprot_generation(const gprot_ctx *ctx);
 
 /* GPRotModel.lnlike(theta) for B proposals in ONE launch (gprot/model.py:358-365 called
  * per walker from Emcee3Model.compute_log_likelihood, gprot/fit.py:20-22):
@@ -101,8 +106,15 @@ const char *gprot_group_last_error(const gprot_group *grp);
 int gprot_group_register_lc(gprot_group *grp, int m, const int *n, const double *t, const double *y,
                             const double *yerr, int *lc_id);
 int gprot_group_unregister_all(gprot_group *grp);
+int gprot_group_unregister_lc(gprot_group *grp, int lc_id);
 int gprot_group_lnlike_batch(gprot_group *grp, int64_t B, const double *theta, const int32_t *lc_id,
                              double *out, unsigned flags);
+/* gprot_lnpost_batch over the devices of the group (prior on the host, rows outside its support not factorised): what a
+ * sampler step calls when GPRotModel runs on a GPGroup (gprot/fit.py:16-22 through pool.map, gprot/model.py:367-369). */
+int gprot_group_lnpost_batch(gprot_group *grp, int64_t B, const double *theta, const int32_t *lc_id,
+                             const double *bounds, const double *mu, const double *sigma, double pmin,
+                             double pmax, const double *mixture, int k, double *out_lnprior,
+                             double *out_lnlike, unsigned flags);
 
 /* Measurement hooks (bench.py): device time of the last likelihood launch, CUDA events on the
  * launching stream; number of kernels launched by this context so far; FP64 tensor (DMMA) peak

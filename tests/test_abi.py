@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound(built):
     for n in names:
         assert hasattr(lib, n), "missing export: " + n
     assert sorted(_lib.SIGNATURES) == names          # the ctypes stub binds exactly the declared surface
-    assert _lib.load().gprot_abi_version() == 1
+    assert _lib.load().gprot_abi_version() == 2
 
 
 def test_no_torch_or_cxx_types_in_header():

@@ -96,3 +96,150 @@ def test_predict_through_the_likelihood(engine):
     assert np.all(np.abs(mu - ref_mu) <= 1e-6 * scale)
     assert np.all(np.abs(var - ref_var) <= 1e-6 * (A + S))
     assert var[2] < 0.1 * (A + S) and var[0] > var[1]                 # on a data point: small; outside the data: larger
+
+
+def test_sampler_steps_through_a_group_engine(engine):
+    """GPRotModel(engine=GPGroup([...])): Ensemble.propose -> lnpost_batch -> gprot_group_lnpost_batch.  On a one-GPU box
+    the group holds two contexts on device 0; the chain must be the one a single engine produces, value for value."""
+    import torch
+
+    from gprotation_b200 import GPGroup
+
+    ndev = torch.cuda.device_count()
+    grp = GPGroup([0, 1 % ndev])
+    try:
+        engine.unregister_all()
+        chains = []
+        for eng in (engine, grp):
+            mod, (t, y, yerr, truth) = _model(eng, n=360, chunksize=120, seed=23)
+            rs = np.random.RandomState(4)
+            ens = em.Ensemble(Emcee3Model(mod), mod.sample_from_prior(20, seed=6), pool=EnsemblePool(), random=rs)
+            sam = em.Sampler([(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)])
+            sam.run(ens, 6)
+            chains.append((sam.get_coords().copy(), sam.backend.log_likelihood.copy(), sam.backend.log_prior.copy()))
+        for a, b in zip(chains[0], chains[1]):
+            assert np.array_equal(a, b)
+        # and the posterior parts agree with the oracle, rows outside the prior masked
+        th = mod.sample_from_prior(7, seed=8)
+        th[3, 0] = 1.0
+        lp, ll = mod.lnpost_batch(th, return_parts=True)
+        assert lp[3] == -np.inf and ll[3] == -np.inf
+        chunks = o.split_chunks(len(t), 120)
+        for i in (0, 5):
+            ref = o.lnlike(th[i], t, y, yerr, chunks)
+            assert abs(ll[i] - ref) <= 1e-9 * abs(ref)
+            assert lp[i] == pytest.approx(o.lnprior(th[i]), rel=1e-12)
+    finally:
+        grp.close()
+
+
+def test_gp_handle_is_the_george_surface_the_reference_uses(engine):
+    """GPRotModel.gp(theta, x, yerr).lnlikelihood(y, quiet=True) (gprot/model.py:336-356) and .predict(y, t)."""
+    engine.unregister_all()
+    t, y, yerr, truth = synthetic_lightcurve(33, 240, baseline=100.0, kind="gp")
+    mod = GPRotModel(LightCurve(t, y, yerr, name="g", chunksize=None), engine=engine)
+    gp = mod.gp(truth)
+    ref = o.lnlike_function(truth, t, y, yerr)
+    assert abs(gp.lnlikelihood(y, quiet=True) - ref) <= 1e-9 * abs(ref)
+    sub = mod.gp(truth, x=t[:100], yerr=yerr[:100])
+    ref = o.lnlike_function(truth, t[:100], y[:100], yerr[:100])
+    assert abs(sub.lnlikelihood(y[:100]) - ref) <= 1e-9 * abs(ref)
+    bad = truth.copy()
+    bad[0] = 800.0
+    assert mod.gp(bad).lnlikelihood(y, quiet=True) == -np.inf
+    with pytest.raises(np.linalg.LinAlgError):
+        mod.gp(bad).lnlikelihood(y)
+    mu, var = gp.predict(y, np.array([t[10], t[-1] + 2.0]))
+    mu2, var2 = mod.predict(truth, np.array([t[10], t[-1] + 2.0]))
+    assert np.allclose(mu, mu2, rtol=1e-9, atol=0) and np.allclose(var, var2, rtol=1e-7, atol=0)
+
+
+def test_registration_hygiene(engine):
+    """Per-light-curve unregister, id validity across unregister_all (generation), the ad-hoc LRU of lnlike_function, the
+    re-registration of a light curve that changed, and the cached problem list with an explicit lc id."""
+    engine.unregister_all()
+    t, y, yerr, truth = synthetic_lightcurve(34, 200, baseline=100.0, kind="harmonic")
+    a = engine.register_lc(t, y, yerr)
+    b = engine.register_lc(t[:150], y[:150], yerr[:150])
+    th = o.sample_from_prior(5, seed=1)
+    want_b = engine.lnlike_batch(th, lc_id=b)
+    engine.unregister_lc(a)
+    assert np.array_equal(engine.lnlike_batch(th, lc_id=b), want_b)          # b keeps its id and its data
+    with pytest.raises(Exception):
+        engine.lnlike_batch(th, lc_id=a)
+    with pytest.raises(Exception):
+        engine.unregister_lc(a)
+    c = engine.register_lc(t, 2 * y, yerr)
+    assert c not in (a, b)
+    # repeated identical calls hit the cached device list: one kernel + one reduction each, same bits
+    l0 = engine.launch_count()
+    for _ in range(3):
+        assert np.array_equal(engine.lnlike_batch(th, lc_id=b), want_b)
+    assert engine.launch_count() - l0 == 6
+    # a model notices that every id became void
+    mod = GPRotModel(LightCurve(t, y, yerr, name="h", chunksize=None), engine=engine)
+    first = mod.lnlike(truth)
+    g0 = engine.generation
+    engine.unregister_all()
+    assert engine.generation == g0 + 1
+    other = engine.register_lc(t[:50], y[:50], yerr[:50])                    # takes id 0: the model must not use it
+    assert mod.lnlike(truth) == first
+    assert mod._lc_id != other
+    # a light curve that changes is registered again, the stale copy dropped
+    mod.lc.y = 3.0 * np.asarray(mod.lc.y)
+    ref = o.lnlike_function(truth, t, 3.0 * y, yerr)
+    assert abs(mod.lnlike(truth) - ref) <= 1e-9 * abs(ref)
+    # ad-hoc arrays: bounded
+    mod._adhoc_max = 4
+    for k in range(9):
+        sl = slice(k, k + 60)
+        got = mod.lnlike_function(truth, t[sl], y[sl], yerr[sl])
+        ref = o.lnlike_function(truth, t[sl], y[sl], yerr[sl])
+        assert abs(got - ref) <= 1e-9 * abs(ref)
+    assert len(mod._adhoc) == 4
+    assert mod.lnlike_function(truth, t[8:68], y[8:68], yerr[8:68]) == got          # a hit, same bits
+    # many registrations with interleaved unregisters: the arena is compacted, ids keep their meaning
+    keep = engine.register_lc(t, y, yerr)
+    base = engine.lnlike_batch(th, lc_id=keep)
+    rng = np.random.default_rng(0)
+    for k in range(40):
+        tt = np.sort(rng.uniform(0, 100, 4000))
+        tmp = engine.register_lc(tt, rng.standard_normal(4000) * 1e-3, np.full(4000, 1e-4))
+        engine.unregister_lc(tmp)
+    assert np.array_equal(engine.lnlike_batch(th, lc_id=keep), base)
+
+
+@pytest.mark.parametrize("cl", [2, 4])
+def test_cluster_kernels_with_invalid_problems_mixed_in(engine, cl):
+    """A chunk with a NaN time stamp (mingap2 < 0) and rows with non-finite theta take the early exit of the cluster
+    kernels; mixed with valid problems in one launch they must neither hang nor disturb the valid rows."""
+    engine.unregister_all()
+    t, y, yerr, truth = synthetic_lightcurve(35, 700, baseline=300.0, kind="harmonic")
+    tb = t.copy()
+    tb[300] = np.nan
+    good = engine.register_lc(t, y, yerr)
+    badlc = engine.register_lc(tb, y, yerr, chunks=o.split_chunks(700, 250))
+    th = o.sample_from_prior(24, seed=2)
+    th[5, 0] = np.nan
+    th[11, 4] = np.inf
+    rows = np.array([badlc if i % 3 == 1 else good for i in range(24)], dtype=np.int32)
+    try:
+        engine.set_cluster(1)
+        ref = engine.lnlike_batch(th, lc_id=rows)
+        engine.set_cluster(cl)
+        for _ in range(5):
+            got = engine.lnlike_batch(th, lc_id=rows)
+            assert engine.last_cluster() == cl
+            assert np.array_equal(got, ref)
+    finally:
+        engine.set_cluster(0)
+    assert np.all(ref[rows == badlc] == -np.inf) and ref[5] == -np.inf and ref[11] == -np.inf
+    ok = [i for i in range(24) if rows[i] == good and i not in (5, 11)]
+
+    def cond(x):
+        ev = np.linalg.eigvalsh(o.kernel_matrix(x, t, yerr))
+        return ev[-1] / ev[0]
+    ok = [i for i in ok if cond(th[i]) <= 1e7][:4]               # the flat bound of tests/test_gpu_parity.py
+    assert len(ok) >= 2
+    want = np.array([o.lnlike_function(th[i], t, y, yerr) for i in ok])
+    assert np.all(np.abs(ref[ok] - want) <= 1e-9 * np.abs(want))

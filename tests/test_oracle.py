@@ -119,3 +119,34 @@ def test_failure_is_minus_inf_never_nan(golden):
 def test_flop_model():
     assert o.flops_per_eval(2048) == pytest.approx(2.8696e9, rel=1e-4)
     assert o.flops_per_eval(8192) == pytest.approx(1.83353e11, rel=1e-4)
+
+
+def test_hodlr_restatement_agrees_with_the_dense_oracle(golden):
+    """oracle/hodlr_oracle.py restates the solver the reference actually uses (george HODLRSolver, nleaf=100, tol=1e-12;
+    gprot/model.py:343).  It approximates the same matrix: the two log-likelihoods differ by O(tol * cond(K))."""
+    from oracle import hodlr_oracle as h
+    from gprotation_b200.synth import synthetic_lightcurve
+
+    for name in ["n150", "n300c100", "n257"]:
+        t, y, yerr = golden[name + "_t"], golden[name + "_y"], golden[name + "_yerr"]
+        cs = int(golden[name + "_chunksize"])
+        chunks = o.split_chunks(len(t), None if cs < 0 else cs)
+        got = np.array([h.lnlike(th, t, y, yerr, chunks) for th in golden[name + "_theta"]])
+        ref, cond = golden[name + "_lnlike"], golden[name + "_cond"]
+        assert np.all(np.abs(got - ref) <= np.maximum(1e-11, 1e-11 * cond) * np.abs(ref)), (name, np.abs(got - ref) / np.abs(ref), cond)
+    # a size where the tree has three levels and the off-diagonal blocks are truly low rank
+    t, y, yerr, truth = synthetic_lightcurve(5, 900, kind="harmonic")
+    th = o.sample_from_prior(3, seed=5)
+    th[0] = truth
+    for x in th:
+        a, b = o.lnlike_function(x, t, y, yerr), h.lnlike_function(x, t, y, yerr)
+        ev = np.linalg.eigvalsh(o.kernel_matrix(x, t, yerr))
+        assert abs(a - b) <= max(1e-11, 1e-11 * ev[-1] / ev[0]) * abs(a)
+    r = h.ranks(th[0], t, yerr)
+    assert max(max(v) for v in r.values()) < 450                      # compressed: well below the block size
+    # failure semantics and permutation (george sorts by x)
+    bad = th[0].copy()
+    bad[0] = 800.0
+    assert h.lnlike_function(bad, t, y, yerr) == -np.inf
+    p = np.random.default_rng(0).permutation(len(t))
+    assert h.lnlike_function(th[0], t[p], y[p], yerr[p]) == pytest.approx(h.lnlike_function(th[0], t, y, yerr), rel=1e-12)
