@@ -32,6 +32,7 @@ class LightCurve(object):
         self.chunksize = chunksize
         self._name = name
         self._x_list = self._y_list = self._yerr_list = None
+        self.version = 0                      # counts every change of the arrays / chunk lists (see _invalidate)
         self._x_full, self._y_full, self._yerr_full = self._x.copy(), self._y.copy(), self._yerr.copy()
         self.sub = sub
         self.subsample(sub)

@@ -283,7 +283,11 @@ class GPRotModel(object):
     # ---- batched siblings: a whole ensemble per launch
     def _prior_args(self):
         mix = self.period_mixture if self.acf_prior else None
-        return np.asarray(self.bounds, dtype=np.float64).reshape(10), self.gp_prior_mu, self.gp_prior_sigma, mix
+        b = getattr(self, "_bounds_flat", None)
+        if b is None or self._bounds_src is not self._bounds:          # flattened once per bounds object, not per call
+            b = self._bounds_flat = np.ascontiguousarray(np.asarray(self.bounds, dtype=np.float64).reshape(10))
+            self._bounds_src = self._bounds
+        return b, self.gp_prior_mu, self.gp_prior_sigma, mix
 
     def lnprior_batch(self, thetas):
         thetas = np.ascontiguousarray(thetas, dtype=np.float64).reshape(-1, 5)

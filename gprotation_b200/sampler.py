@@ -422,13 +422,12 @@ class KDEMove(RedBlueMove):
 
     @staticmethod
     def _logpdf(x, data, chol):
-        # log (1/n) sum_j N(x - data_j; C),  C = chol chol^T
+        # log (1/n) sum_j N(x - data_j; C),  C = chol chol^T.  |L^-1 (x - d)|^2 = |L^-1 x|^2 + |L^-1 d|^2 - 2 (L^-1 x).(L^-1 d):
+        # two small matrix products instead of a [m, n, d] triangular solve
         n, d = data.shape
-        from scipy.linalg import solve_triangular
-
-        diff = x[:, None, :] - data[None, :, :]                                       # [m, n, d]
-        y = solve_triangular(chol, diff.reshape(-1, d).T, lower=True).T.reshape(len(x), n, d)
-        e = -0.5 * np.sum(y * y, axis=2)
+        linv = np.linalg.inv(chol)
+        xs, ds = x @ linv.T, data @ linv.T
+        e = -0.5 * (np.einsum("ij,ij->i", xs, xs)[:, None] + np.einsum("ij,ij->i", ds, ds)[None, :] - 2.0 * (xs @ ds.T))
         mx = np.max(e, axis=1, keepdims=True)
         lse = mx[:, 0] + np.log(np.sum(np.exp(e - mx), axis=1))
         return lse - np.log(n) - 0.5 * d * np.log(2 * np.pi) - np.sum(np.log(np.diag(chol)))
@@ -436,10 +435,12 @@ class KDEMove(RedBlueMove):
     def get_proposal(self, ensemble, s, c):
         n, d = c.shape
         factor = n ** (-1.0 / (d + 4)) if self.bw_method is None else float(self.bw_method)
-        chol = np.linalg.cholesky(np.atleast_2d(np.cov(c, rowvar=False)) * factor ** 2)
+        dc = c - c.mean(axis=0)
+        chol = np.linalg.cholesky((dc.T @ dc) * (factor ** 2 / (n - 1.0)))          # = cov(c) * factor^2
         pick = ensemble.random.randint(n, size=len(s))
         q = c[pick] + ensemble.random.randn(len(s), d) @ chol.T
-        return q, self._logpdf(s, c, chol) - self._logpdf(q, c, chol)
+        lp = self._logpdf(np.concatenate([s, q]), c, chol)
+        return q, lp[: len(s)] - lp[len(s):]
 
 
 # ------------------------------------------------------------------------------------------ sampler
@@ -457,6 +458,7 @@ class Sampler(object):
         else:
             self._moves, self._weights = [moves], [1.0]
         self._weights = np.asarray(self._weights) / np.sum(self._weights)
+        self._cumw = np.cumsum(self._weights)
         self.backend = Backend() if backend is None else backend
 
     def reset(self):
@@ -467,7 +469,7 @@ class Sampler(object):
             self.backend.extend(niter // thin, ensemble.nwalkers, ensemble.ndim)
         i = 0
         while niter is None or i < niter:
-            move = self._moves[ensemble.random.choice(len(self._moves), p=self._weights)]
+            move = self._moves[min(int(np.searchsorted(self._cumw, ensemble.random.rand(), side="right")), len(self._moves) - 1)]
             ensemble = move.update(ensemble)
             if store and (i + 1) % thin == 0:
                 self.backend.update(ensemble)
