@@ -34,6 +34,8 @@ constexpr int STAGES = 4;         // TMA pipeline depth; one stage = A slab + B 
 constexpr int LDM = 132;          // row pitch of the diagonal-block workspace (== 4 mod 16: conflict-free fragments)
 constexpr int REGION_A = 128 * LDM;   // doubles; >= STAGES * 2 * SLAB
 constexpr int W_DOUBLES = 9216;   // packed fragment-major lower triangle of W (72 KB)
+constexpr int WBUFS = 4;          // cluster kernels: exchange buffers for W_J, z_J (a CTA may run up to WBUFS - 1 columns ahead)
+__host__ __device__ constexpr int cctr_ints(int tcap) { return 3 * tcap + 8; }   // [0] fail, [1] diagdone, [2..] row counters, rowdone, coldone
 
 struct Hyp {
     double A, L, G, S, P;   // exp(theta)
@@ -82,9 +84,9 @@ struct Params {
     double* vscratch;             // per-slot vectors: t (clamped), sin, cos, diag, ytilde (5 * npad_max)
     int npad_max;
     long long* timing;            // [16] per-phase cycle totals of CTA 0 (only written when built with -DGPROT_TIMING)
-    double* wg;                   // cluster kernels, per slot: 2 x [W | z] exchange buffers, then per-column sums (2 x tcap)
+    double* wg;                   // cluster kernels, per slot: WBUFS x [W | z] exchange buffers, then per-column sums (2 x tcap)
     size_t wg_stride;             // doubles
-    int* cctr;                    // cluster kernels, per slot: failure flag + per-column row counters (2 + tcap ints)
+    int* cctr;                    // cluster kernels, per slot: CCTR_INTS(tcap) ints of flags and counters (see the cluster path)
     int tcap;                     // capacity in block columns of the per-column arrays
 };
 
@@ -144,6 +146,13 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// flags in global memory between the CTAs that share a problem (release / acquire at gpu scope)
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void dsmem_store_int(int* local, uint32_t peer, int v) {
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(peer));
@@ -893,9 +902,10 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         }
         const bool white_off = mingap2 < h.thr;
         for (int i = crank * NT + tid; i < npad; i += CL * NT) point_vectors(i, n, t, y, yerr, h, vt, vs, vc, vd, yw);
-        if (CL > 1 && crank == 0) {                              // failure flag and per-column row counters of this problem
-            int* const ctr0 = prm.cctr + (size_t)slot * (prm.tcap + 2);
-            for (int i = tid; i < T + 1; i += NT) ctr0[i] = 0;
+        if (CL > 1 && crank == 0) {                              // flags and counters of this problem (layout: the cluster path below)
+            int* const ctr0 = prm.cctr + (size_t)slot * cctr_ints(prm.tcap);
+            for (int i = tid; i < 2 + T; i += NT) ctr0[i] = 0;                               // fail, diagdone, row counters
+            for (int i = tid; i < T; i += NT) { ctr0[2 + prm.tcap + i] = 0; ctr0[2 + 2 * prm.tcap + i] = 0; }   // rowdone, coldone
         }
         if (CL > 1) cluster_sync(); else __syncthreads();
         TICK(0);
@@ -935,7 +945,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                             v.y = (active && r >= c + 1) ? -acc[mi][ni][1] : ((wr >= ractJ && r == c + 1) ? 1.0 : 0.0);
                             *reinterpret_cast<double2*>(M + r * LDM + c) = v;
                         }
-                    if (tid < BS) sm.yj[tid] = yw[J * BS + tid];
+                    if (tid < BS) sm.yj[tid] = CL > 1 ? __ldcg(yw + J * BS + tid) : yw[J * BS + tid];
                 }
                 __syncthreads();
                 TICK(3);
@@ -982,7 +992,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             const bool pf = nextI >= 0 && tid < 3 * BS;
             double pv = 0.0, ycur = 0.0;
             if (pf) pv = vt[(size_t)(tid >> 7) * prm.npad_max + nextI * BS + (tid & (BS - 1))];
-            if (tid < 32 * ract) ycur = yw[I * BS + tid];
+            if (tid < 32 * ract) ycur = CL > 1 ? __ldcg(yw + I * BS + tid) : yw[I * BS + tid];   // CL > 1: written by another SM
             if (rowact) {
                 if (I * BS + BS <= n && !white_off) synth_tile<EXACT, false>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
                 else                                synth_tile<EXACT, true>(acc, sm, 32 * wr, 32 * wc, I * BS + 32 * wr, J * BS + 32 * wc, n, vd, white_off, lane);
@@ -1039,10 +1049,34 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             // others work on column J (look-ahead), publishes W_{J+1}, z_{J+1} and the column's partial sums through
             // global scratch, and comes back for more rows.  Every block is computed by exactly one CTA with the same
             // arithmetic as in the one-CTA kernel, and the sums are added in column order: bitwise the same result.
-            double* const wg = prm.wg + (size_t)slot * prm.wg_stride;             // 2 x [W | z], then qcol[], lcol[]
-            double* const qcol = wg + 2 * (W_DOUBLES + BS);
+            //
+            // There is no barrier between columns.  Block (I, J) needs the blocks (I, k < J) of its row, the blocks of
+            // row J and W_J, z_J: each block row I carries a counter rowdone[I] = number of its columns that are complete
+            // and visible, diagdone = the last diagonal block that has been published, both written with release and
+            // polled with acquire by thread 0.  A CTA that finds no row left in column J moves on to column J+1 at once
+            // and starts on the rows whose column-J blocks are already there.  Waits only ever point to earlier columns
+            // (or to a CTA that is computing, not waiting), so they cannot cycle; the cluster launch guarantees that all
+            // CTAs of the group are resident.  A failed pivot raises `fail`, which every wait also watches.
+            double* const wg = prm.wg + (size_t)slot * prm.wg_stride;             // WBUFS x [W | z], then qcol[], lcol[]
+            double* const qcol = wg + WBUFS * (W_DOUBLES + BS);
             double* const lcol = qcol + prm.tcap;
-            int* const ctr = prm.cctr + (size_t)slot * (prm.tcap + 2);            // [0] failure flag, [1 + J] row counters
+            int* const ctr = prm.cctr + (size_t)slot * cctr_ints(prm.tcap);
+            int* const failflag = ctr;                                             // a pivot failed somewhere
+            int* const diagdone = ctr + 1;                                         // number of diagonal blocks whose W_J, z_J, sums are published
+            int* const rowctr = ctr + 2;                                           // [J] next block row of column J to hand out
+            int* const rowdone = ctr + 2 + prm.tcap;                               // [I] columns of block row I complete (incl. ytilde_I)
+            int* const coldone = ctr + 2 + 2 * prm.tcap;                           // [J] CTAs that have left column J
+            auto wait_for = [&](const int* flag, const int want) -> bool {         // false: the problem failed meanwhile
+                if (tid == 0) {
+                    int bad = 0;
+                    while (ld_acquire(flag) < want && !(bad = ld_acquire(failflag))) __nanosleep(32);
+                    sm.prob2 = bad ? 1 : 0;
+                }
+                __syncthreads();
+                const bool ok = sm.prob2 == 0;
+                __syncthreads();                                                   // sm.prob2 is reused right away
+                return ok;
+            };
             auto publish_w = [&](const int buf) {
                 double* dst = wg + (size_t)buf * (W_DOUBLES + BS);
                 for (int i = tid; i < W_DOUBLES / 2; i += NT) reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(sm.W)[i];
@@ -1057,57 +1091,73 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             stage_points(sm.colv, vt, prm.npad_max, 0, tid);
             stage_points(sm.rowv, vt, prm.npad_max, 0, tid);
             __syncthreads();
-            if (!diag_block(0, -1)) failed = true;
-            if (!failed && crank == 0) {
-                if (tid == 0) column_sums(qcol[0], lcol[0]);
-                publish_w(0);
+            if (!diag_block(0, -1)) {
+                failed = true;
+                if (tid == 0) { atomicExch(failflag, 1); sm.fail = 0; }
             }
-            __threadfence();
-            cluster_sync();
+            if (!failed && crank == 0) {                                       // W_0 for the CTA that comes back to column 0 after
+                if (tid == 0) column_sums(qcol[0], lcol[0]);                    // forming the second diagonal block
+                publish_w(0);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) st_release(diagdone, 1);
+            }
+            __syncthreads();
             for (int J = 0; J < T && !failed; J++) {
                 if (J > 0) {
-                    if (__ldcg(ctr) != 0) { failed = true; break; }           // a pivot of column J failed (same answer in every CTA)
-                    fetch_w(J & 1);
+                    if (!wait_for(diagdone, J + 1)) { failed = true; break; }  // W_J, z_J are there (and row J is complete)
+                    fetch_w(J % WBUFS);
                     stage_points(sm.colv, vt, prm.npad_max, J, tid);
                     __syncthreads();
                 }
                 for (;;) {
-                    if (tid == 0) sm.prob2 = atomicAdd(ctr + 1 + J, 1);
+                    if (tid == 0) sm.prob2 = atomicAdd(rowctr + J, 1);
                     __syncthreads();
                     const int I = J + 1 + sm.prob2;
+                    __syncthreads();
                     if (I >= T) break;
+                    if (!wait_for(rowdone + I, J)) { failed = true; break; }   // blocks (I, 0 .. J-1) and ytilde_I through column J-1
+                    if (tid == 0) fence_async();                               // ... before this CTA's TMA reads them
                     offdiag_block(I, J, -1, false);
+                    __threadfence();                                           // L_IJ and ytilde_I, then the row's counter
+                    fence_async();
+                    __syncthreads();
+                    if (tid == 0) st_release(rowdone + I, J + 1);
                     if (I == J + 1) {
-                        __threadfence();                                       // L_{J+1,J} and ytilde_{J+1} before this CTA's own TMA reads
-                        fence_async();
-                        __syncthreads();
                         stage_points(sm.colv, vt, prm.npad_max, J + 1, tid);
                         stage_points(sm.rowv, vt, prm.npad_max, J + 1, tid);
                         __syncthreads();
                         const bool ok = diag_block(J + 1, -1);
                         if (ok) {
+                            // buffer (J+1) % WBUFS last held W_{J+1-WBUFS}: every CTA must have left that column
+                            if (J + 1 >= WBUFS && !wait_for(coldone + (J + 1 - WBUFS), CL)) { failed = true; break; }
                             if (tid == 0) column_sums(qcol[J + 1], lcol[J + 1]);
-                            publish_w((J + 1) & 1);
-                        } else if (tid == 0) {
-                            atomicExch(ctr, 1);
-                            sm.fail = 0;
+                            publish_w((J + 1) % WBUFS);
+                            __threadfence();
+                            __syncthreads();
+                            if (tid == 0) st_release(diagdone, J + 2);
+                        } else {
+                            if (tid == 0) { atomicExch(failflag, 1); sm.fail = 0; }
+                            failed = true;
+                            break;
                         }
-                        __syncthreads();
                         if (J + 2 < T) {                                       // back to column J: its W, z and column points
-                            fetch_w(J & 1);
+                            if (!wait_for(diagdone, J + 1)) { failed = true; break; }   // (J = 0: rank 0 publishes W_0)
+                            fetch_w(J % WBUFS);
                             stage_points(sm.colv, vt, prm.npad_max, J, tid);
                         }
+                        __syncthreads();
                     }
-                    __syncthreads();
                 }
-                __threadfence();
-                fence_async();
-                cluster_sync();
-                fence_async();
+                if (failed) break;
+                if (tid == 0) atomicAdd(coldone + J, 1);                        // this CTA no longer needs W_J
                 TICK(11);
             }
-            if (tid == 0 && crank == 0 && !failed) {
-                for (int J = 0; J < T; J++) { quad += __ldcg(qcol + J); logdet += __ldcg(lcol + J); }
+            if (crank == 0) {                                                   // rank 0 reports: wait for the last diagonal block
+                if (!failed && !wait_for(diagdone, T)) failed = true;
+                if (!failed && ld_acquire(failflag)) failed = true;
+                if (tid == 0 && !failed)
+                    for (int J = 0; J < T; J++) { quad += __ldcg(qcol + J); logdet += __ldcg(lcol + J); }
             }
         }
         if (tid == 0 && crank == 0) prm.prob_out[prob] = finish_lnlike(quad, logdet, n, failed);

@@ -478,7 +478,7 @@ int plan_launch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
 }
 
 constexpr int TCAP = 1024;                                   // block columns the cluster kernels can track (N <= 131072)
-constexpr size_t WG_STRIDE = 2 * (size_t)(W_DOUBLES + BS) + 2 * TCAP;
+constexpr size_t WG_STRIDE = WBUFS * (size_t)(W_DOUBLES + BS) + 2 * TCAP;
 
 // factor scratch, per-point vectors and (cluster kernels) the W exchange buffers, grown on demand; may lower lp.slots to
 // what fits in device memory
@@ -494,7 +494,7 @@ int ensure_scratch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
         size_t freeb = 0, totalb = 0;
         CU(ctx, cudaMemGetInfo(&freeb, &totalb));
         // per slot: the factor scratch, the per-point vectors and (cluster kernels) the W exchange buffers allocated below
-        const size_t per_slot = s2 * 8 + (size_t)5 * std::max(lp.npad, ctx->v_npad) * 8 + WG_STRIDE * 8 + (TCAP + 2) * 4;
+        const size_t per_slot = s2 * 8 + (size_t)5 * std::max(lp.npad, ctx->v_npad) * 8 + WG_STRIDE * 8 + (size_t)cctr_ints(TCAP) * 4;
         const size_t budget = (size_t)(0.85 * (double)freeb);
         ctx->max_lslots = 0;
         if ((size_t)want * per_slot > budget) {
@@ -526,7 +526,7 @@ int ensure_scratch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
             ctx->d_wg = nullptr; ctx->d_cctr = nullptr;
             const int want = std::max(lp.slots, ctx->num_sms / 2);
             CU(ctx, cudaMalloc((void**)&ctx->d_wg, (size_t)want * WG_STRIDE * 8));
-            CU(ctx, cudaMalloc((void**)&ctx->d_cctr, (size_t)want * (TCAP + 2) * 4));
+            CU(ctx, cudaMalloc((void**)&ctx->d_cctr, (size_t)want * cctr_ints(TCAP) * 4));
             ctx->cslots = want;
         }
     }
