@@ -324,7 +324,7 @@ def run_config3(eng, torch, dist, rank, world, local, peak_tf, args):
     """configs[3]: ONE star, N=8192, 256 walker proposals; the ensemble is split over the ranks (32 rows per GPU at 8 GPUs,
     each problem spread over a thread-block cluster) and every rank ends the step holding all 256 log-likelihoods: the
     NCCL all-gather is inside the timed region.  Strong scaling: the work is fixed as N grows."""
-    from gprotation_b200.dist import shard_bounds
+    from gprotation_b200.dist import all_gather_rows, gather_width, ordered_rows, shard_bounds
     from gprotation_b200.synth import synthetic_lightcurve
     from oracle import gp_oracle as o
 
@@ -333,7 +333,7 @@ def run_config3(eng, torch, dist, rank, world, local, peak_tf, args):
     lc = eng.register_lc(t, y, yerr)
     th = o.sample_from_prior(B, seed=9)
     lo, hi = shard_bounds(B, rank, world)
-    width = -(-B // world)
+    width = gather_width(B, world)
     stream = torch.cuda.current_stream()
     d_th = torch.from_numpy(np.ascontiguousarray(th[lo:hi])).cuda()
     d_loc = torch.full((width,), float("nan"), dtype=torch.float64, device="cuda")
@@ -342,15 +342,11 @@ def run_config3(eng, torch, dist, rank, world, local, peak_tf, args):
     def step():
         if hi > lo:
             eng.lnlike_batch_device(d_th.data_ptr(), hi - lo, d_loc.data_ptr(), lc_id=lc, stream=stream.cuda_stream)
-        if dist is not None:
-            dist.all_gather_into_tensor(d_all, d_loc)
-        else:
-            d_all.copy_(d_loc)
+        all_gather_rows(d_loc, B, world, out=d_all)              # NCCL all-gather of the log-likelihoods (a copy at N = 1)
 
     sec = _timed_steps(torch, dist, stream, step, reps=args.c3_reps)
     cl = eng.last_cluster()
-    full = d_all.cpu().numpy().reshape(world, width)
-    res = np.concatenate([full[r][: shard_bounds(B, r, world)[1] - shard_bounds(B, r, world)[0]] for r in range(world)])
+    res = ordered_rows(d_all, B, world)
     F = flops_per_eval(n)
     out = {"workload": "configs[3]: 1 star, N=%d, %d walkers split over %d GPU(s), NCCL all-gather inside the timed region" % (n, B, world),
            "scaling": "strong", "value": B / sec, "unit": "evals/s", "seconds_per_ensemble": sec, "rows_per_gpu": hi - lo,

@@ -44,3 +44,37 @@ def sharded_lnlike(evaluate, thetas, lc_id=None, rank=0, world=1, gather=True, d
         a, b = shard_bounds(B, r, world)
         out[a:b] = recv[r][: b - a].cpu().numpy()
     return out
+
+
+def gather_width(nitems, world):
+    """Rows per rank of the padded all-gather buffer (the largest block of shard_bounds)."""
+    return -(-int(nitems) // int(world))
+
+
+def all_gather_rows(local, nitems, world, out=None):
+    """All-gather of the per-rank blocks of a block-sharded vector of ``nitems`` rows (torch tensors on the device of
+    the process group: NCCL on the GPU box, gloo on CPU).  ``local`` holds this rank's block in its first rows, padded to
+    ``gather_width``; returns the padded [world * width] buffer (``ordered_rows`` puts the rows back in order).  This
+    is the one collective of the path: the log-probabilities of a single star's ensemble that spans GPUs
+    (scripts/gprot-fit:127-131,195: the reference gathers them through pool.map)."""
+    import torch
+    import torch.distributed as dist
+
+    width = gather_width(nitems, world)
+    if out is None:
+        out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    if world == 1:
+        out.copy_(local)
+        return out
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(out, local)
+    else:
+        dist.all_gather(list(out.view(world, width).unbind(0)), local)
+    return out
+
+
+def ordered_rows(gathered, nitems, world):
+    """The ``nitems`` rows of an ``all_gather_rows`` buffer, in their original order (NumPy array)."""
+    width = gather_width(nitems, world)
+    g = gathered.detach().cpu().numpy().reshape(world, width)
+    return np.concatenate([g[r][: shard_bounds(nitems, r, world)[1] - shard_bounds(nitems, r, world)[0]] for r in range(world)])

@@ -125,3 +125,42 @@ def test_sharded_lnlike_two_ranks_gloo():
         assert np.allclose(full, want, rtol=0, atol=0)
         lo, hi = shard_bounds(13, rank, 2)
         assert np.array_equal(local, want[lo:hi])
+
+
+def _gather_worker(rank, world, port, q, nitems):
+    import torch
+    import torch.distributed as dist
+
+    from gprotation_b200.dist import all_gather_rows, gather_width, ordered_rows
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_bounds(nitems, rank, world)
+    local = torch.full((gather_width(nitems, world),), float("nan"), dtype=torch.float64)
+    local[: hi - lo] = torch.arange(lo, hi, dtype=torch.float64) * 1.5 - 7.0          # this rank's block of "log-likelihoods"
+    out = all_gather_rows(local, nitems, world)
+    q.put((rank, ordered_rows(out, nitems, world)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nitems", [256, 13, 2])
+def test_strong_scaling_gather_two_ranks_gloo(nitems):
+    """bench.py extra.config3 (one star's ensemble split over the ranks): the block split, the padded all-gather and the
+    re-ordering, world_size 2 over gloo -- uneven blocks and fewer rows than a full block included."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + nitems % 7
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q, nitems)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(nitems) * 1.5 - 7.0
+    for _, full in res:
+        assert np.array_equal(full, want)
