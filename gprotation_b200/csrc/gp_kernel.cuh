@@ -34,7 +34,8 @@ constexpr int STAGES = 4;         // TMA pipeline depth; one stage = A slab + B 
 constexpr int LDM = 132;          // row pitch of the diagonal-block workspace (== 4 mod 16: conflict-free fragments)
 constexpr int REGION_A = 128 * LDM;   // doubles; >= STAGES * 2 * SLAB
 constexpr int W_DOUBLES = 9216;   // packed fragment-major lower triangle of W (72 KB)
-constexpr int WBUFS = 4;          // cluster kernels: exchange buffers for W_J, z_J (a CTA may run up to WBUFS - 1 columns ahead)
+constexpr int WBUFS = 4;          // cluster kernels: exchange buffers for W_J, z_J, L_pp (a CTA may run up to WBUFS - 1 columns ahead)
+constexpr int WX_DOUBLES = W_DOUBLES + BS + 16 * 64;   // one exchange buffer: W | z | L_pp tiles
 __host__ __device__ constexpr int cctr_ints(int tcap) { return 3 * tcap + 8; }   // [0] fail, [1] diagdone, [2..] row counters, rowdone, coldone
 
 struct Hyp {
@@ -51,6 +52,7 @@ struct Smem {
     double yj[BS];                // ytilde_J
     double dinv[BS];              // 1 / diag(L_JJ)
     double wt[128];               // inverse of the current / next 8 x 8 diagonal tile (double buffered)
+    double lpp[16 * 64];          // the 8 x 8 diagonal tiles L_pp of L_JJ, row-major (= tile-major operand layout), zero above the diagonal
     double lpart[16];             // per-warp partial sums of log diag(L_JJ)
     double etab[64];              // 2^(j/64)
     double colv[3 * BS];          // block column J: t, sin, cos of the reduced phase
@@ -63,6 +65,8 @@ struct Smem {
     int fail;
     int prob2;                    // block row handed out by the per-column counter (cluster kernels)
 };
+
+static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt into on sm_100a");
 
 struct Params {
     // packed light-curve arena (all registered chunks back to back)
@@ -401,7 +405,7 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
 // Pivot-tile factorisation without shuffles: every lane of the pivot warp holds the whole lower triangle and runs the
 // same elimination (the dependent chain is rsqrt -> scale -> one DFMA per pivot); lane b < 8 then forms column b of
 // the inverse by forward substitution.  Needs ~100 registers, which only the pivot warp's own loop can afford.
-// Outputs: W_pp (sm.wt[buf] and its place in sm.W), 1/diag (sm.dinv).
+// Outputs: W_pp (sm.wt[buf] and its place in sm.W), L_pp (sm.lpp), 1/diag (sm.dinv).
 template <class G, class SM>
 __device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lane) {
     const double* Mp = sm.regionA + (8 * p) * G::LD + 8 * p;
@@ -416,6 +420,9 @@ __device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lan
         }
     }
     double rinv[8];
+    double lcol[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // column (lane & 7) of L_pp, picked up as the columns are finished
+    double dsel = 1.0;                                         // pivot of that column
+    const int b = lane & 7;
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -423,15 +430,17 @@ __device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lan
         if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
         const double ri = rsqrt_pos(d);
         rinv[j] = ri;
+        dsel = (b == j) ? d : dsel;
 #pragma unroll
         for (int a = j + 1; a < 8; a++) l[a][j] *= ri;
+#pragma unroll
+        for (int a = j + 1; a < 8; a++) lcol[a] = (b == j) ? l[a][j] : lcol[a];
 #pragma unroll
         for (int a = j + 1; a < 8; a++)
 #pragma unroll
             for (int b = j + 1; b <= a; b++) l[a][b] = fma(-l[a][j], l[b][j], l[a][b]);
     }
-    // 1/l_jj: rinv is 1/sqrt(d) to ~1 ulp, which is what the in-warp variant stores as well (inv[j] * ri with inv = 1)
-    const int b = lane & 7;
+    // 1/l_jj: rinv is 1/sqrt(d) to ~1 ulp
     double w[8];
 #pragma unroll
     for (int a = 0; a < 8; a++) {
@@ -442,10 +451,14 @@ __device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lan
     }
     if (lane < 8) {
         double* wt = sm.wt + 64 * buf;
+        double* lp = sm.lpp + 64 * p;
+        double ldiag = dsel * w[b];                            // l_bb = sqrt(d_b) = d_b / sqrt(d_b), one Newton step: <= 1 ulp
+        ldiag = fma(fma(-ldiag, ldiag, dsel), 0.5 * w[b], ldiag);
 #pragma unroll
         for (int a = 0; a < 8; a++) {
             wt[a * 8 + b] = w[a];
             sm.W[G::woff(8 * p + a, 8 * p + b)] = w[a];
+            lp[a * 8 + b] = (a > b) ? lcol[a] : ((a == b) ? ldiag : 0.0);     // L_pp for the refinement of the tile solves
         }
         sm.dinv[8 * p + b] = w[b];
     }
@@ -495,31 +508,40 @@ __device__ __forceinline__ void row_sync(int wr, int count) {
     }
 }
 
-// X = M(R, p) W_pp^T for one tile row, rewritten in place; rows above the pivot (R < p) also deliver the finished
-// tile of W^T to sm.W.  Returns the A fragment of -X.
+// X = M(R, p) L_pp^-T for one tile row below the pivot (R > p), rewritten in place.  Returns the A fragment of -X.
+// The product with the explicit inverse W_pp is only a first guess X0: its backward error is eps * cond(L_pp), which
+// costs a digit where neighbouring points are strongly correlated (cond of an 8 x 8 tile reaches 1e7).  One step of
+// iterative refinement on the tensor pipe, X = X0 + (M - X0 L_pp^T) W_pp^T, brings the tile solve to the accuracy of a
+// substitution (tools/emulate_trsm.py; profiles/r02_trsm_emulation.log).
 template <class G, class SM>
-__device__ __forceinline__ void panel_scale(SM& sm, double* row, const double* wt, int R, int p, int g, int q, double& a0, double& a1) {
+__device__ __forceinline__ void panel_scale(SM& sm, double* row, const double* wt, int p, int g, int q, double& a0, double& a1) {
     const double x0 = row[q], x1 = row[q + 4];
+    const double2 m = *reinterpret_cast<const double2*>(row + 2 * q);          // M[g][2q], M[g][2q+1]: C-fragment of the tile
     const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
     double c0 = 0.0, c1 = 0.0;
     dmma(c0, c1, x0, b0);
     dmma(c0, c1, x1, b1);
+    const double2 lp = *reinterpret_cast<const double2*>(sm.lpp + 64 * p + g * 8 + 2 * q);   // L_pp[g][2q], [2q+1] as a B operand
+    const double2 wv = *reinterpret_cast<const double2*>(wt + g * 8 + 2 * q);                // W_pp[g][2q], [2q+1]
+    double r0 = m.x, r1 = m.y;
+    dmma(r0, r1, -c0, lp.x);                                                   // R = M - X0 L_pp^T  (a C fragment is an A operand)
+    dmma(r0, r1, -c1, lp.y);
+    dmma(c0, c1, r0, wv.x);                                                    // X = X0 + R W_pp^T
+    dmma(c0, c1, r1, wv.y);
     __syncwarp();
     *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
-    if (R < p) {                                               // W[8p + 2q + e][8R + g]
-        sm.W[G::woff(8 * p + 2 * q, 8 * R + g)] = c0;
-        sm.W[G::woff(8 * p + 2 * q + 1, 8 * R + g)] = c1;
-    }
     __syncwarp();
     a0 = -row[q]; a1 = -row[q + 4];
 }
 
-// Warp 0 is the pivot warp: it only factors and inverts the 8 x 8 pivot tiles (and scales tile row 0, which stays in
-// shared memory).  Warps 1..15 own tile rows 1..15.  The two roles are separate loops, so the pivot-tile registers and
-// the row accumulators never coexist; they meet at the two block barriers of every step, and the owner of tile row p+1
-// hands the finished pivot tile to warp 0 through named barrier 1 (then updates row 0 while warp 0 factors).
-// nsteps < 16: rows 8 nsteps .. 127 of the block are identity padding; the sweep stops early and diag_pad_identity
-// fills their part of W.  Ends with a block barrier.
+// Warp 0 is the pivot warp: it only factors and inverts the 8 x 8 pivot tiles.  Warps 1..NR-1 own tile rows 1..NR-1.
+// The two roles are separate loops, so the pivot-tile registers and the row accumulators never coexist; they meet at
+// the two block barriers of every step, and the owner of tile row p+1 hands the finished pivot tile to warp 0 through
+// named barrier 1.  Only L_JJ and the pivot-tile inverses W_pp are formed -- every solve with L_JJ is a substitution
+// over the tiles, no inverse of the block exists.  The forward solve z_J = L_JJ^-1 ytilde_J rides along: warp 0 forms
+// z_p = W_pp ytilde_p right after the pivot tile (sm.zs), every row warp subtracts L(R, p) z_p from its rows of ytilde.
+// nsteps < NR: rows 8 nsteps .. of the block are identity padding; the sweep stops early and diag_pad_identity fills
+// their part of the operator.  Ends with a block barrier.
 template <class G, class SM>
 __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int nsteps) {
     constexpr int LD = G::LD, NR = G::NR;
@@ -529,10 +551,12 @@ __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int
         tile8_factor_all<G>(sm, 0, 0, lane);
         __syncthreads();
         for (int p = 0; p < nsteps; p++) {
-            TS(p, 0);
-            if (p >= 1) {
-                double a0, a1;
-                panel_scale<G>(sm, M + g * LD + 8 * p, sm.wt + 64 * (p & 1), 0, p, g, q, a0, a1);
+            {                                                  // z_p = W_pp ytilde_p while the row warps scale their panel tiles
+                const double* wrow = sm.wt + 64 * (p & 1) + 8 * (lane & 7);    // row of W_pp, zero above the diagonal
+                double z = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) z = fma(wrow[k], sm.yj[8 * p + k], z);
+                if (lane < 8) sm.zs[8 * p + lane] = z;
             }
             TS(p, 1);
             __syncthreads();
@@ -548,7 +572,7 @@ __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int
     }
     const int R = warp;
     double* myrow = M + (8 * R + g) * LD;
-    double rt[NR][2];                                          // rt[C] = C fragment of tile (R, C), C >= 2
+    double rt[NR][2];                                          // rt[C] = C fragment of tile (R, C), 2 <= C <= R
 #pragma unroll
     for (int C = 2; C < NR; C++) {
         if (C <= R) {
@@ -556,70 +580,54 @@ __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int
             rt[C][0] = v.x; rt[C][1] = v.y;
         } else { rt[C][0] = 0.0; rt[C][1] = 0.0; }
     }
+    double yR = sm.yj[8 * R + g];                              // ytilde of this lane's row, updated as the columns finish
     __syncthreads();
     for (int p = 0; p < nsteps; p++) {
         const int P0 = 8 * p;
         const double* wt = sm.wt + 64 * (p & 1);
-        double a0, a1;                                         // A fragment of -X(R)
-        if (R != p) panel_scale<G>(sm, myrow + P0, wt, R, p, g, q, a0, a1);
-        else { a0 = -wt[q * 8 + g]; a1 = -wt[(q + 4) * 8 + g]; }     // rows of the pivot tile act through W_pp^T
-        __syncthreads();                                       // X(C), C > p, visible to every warp
+        double a0 = 0.0, a1 = 0.0;                             // A fragment of -X(R)
+        if (R > p) panel_scale<G>(sm, myrow + P0, wt, p, g, q, a0, a1);
+        __syncthreads();                                       // X(C), C > p, and z_p visible to every warp
         if (p == nsteps - 1) break;
-        const int chi = (R <= p) ? NR - 1 : R;                     // tiles p+1 .. chi of this row take the rank-8 update
-        const double* bcol = M + g * LD + P0;                 // B fragments: X(C) at bcol + 8 C LDM
-        {                                                      // the next panel column lives in shared memory
-            double2* cp = reinterpret_cast<double2*>(myrow + P0 + 8 + 2 * q);
-            double2 c = *cp;
-            const double b0 = bcol[8 * (p + 1) * LD + q], b1 = bcol[8 * (p + 1) * LD + q + 4];
-            dmma(c.x, c.y, a0, b0);
-            dmma(c.x, c.y, a1, b1);
-            *cp = c;
-        }
-        if (R == p + 1) {
-            __syncwarp();
-            __threadfence_block();
-            named_arrive(1, 64);                               // hand the pivot tile to warp 0
-            // tile row 0 (kept in shared memory): tiles (0, C), C = p+1 .. 15
-            double r0, r1;
-            if (p == 0) { r0 = -wt[q * 8 + g]; r1 = -wt[(q + 4) * 8 + g]; }
-            else { r0 = -M[g * LD + P0 + q]; r1 = -M[g * LD + P0 + q + 4]; }
-            const double* bp = bcol + 8 * (p + 1) * LD + q;
-            double* cp = M + g * LD + P0 + 8 + 2 * q;
-            int C = p + 1;
-            for (; C + 1 <= NR - 1; C += 2, bp += 16 * LD, cp += 16) {
-                const double b00 = bp[0], b01 = bp[4], b10 = bp[8 * LD], b11 = bp[8 * LD + 4];
-                double2 x = *reinterpret_cast<double2*>(cp), y = *reinterpret_cast<double2*>(cp + 8);
-                dmma(x.x, x.y, r0, b00);
-                dmma(y.x, y.y, r0, b10);
-                dmma(x.x, x.y, r1, b01);
-                dmma(y.x, y.y, r1, b11);
-                *reinterpret_cast<double2*>(cp) = x;
-                *reinterpret_cast<double2*>(cp + 8) = y;
+        if (R > p) {                                           // rows at or above the pivot are finished
+            {                                                  // forward solve, fused: ytilde_R -= L(R, p) z_p
+                double part = fma(a0, sm.zs[P0 + q], a1 * sm.zs[P0 + q + 4]);
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                yR += part;
             }
-            if (C <= NR - 1) {
-                const double b00 = bp[0], b01 = bp[4];
-                double2 x = *reinterpret_cast<double2*>(cp);
-                dmma(x.x, x.y, r0, b00);
-                dmma(x.x, x.y, r1, b01);
-                *reinterpret_cast<double2*>(cp) = x;
+            const double* bcol = M + g * LD + P0;              // B fragments: X(C) at bcol + 8 C LDM
+            {                                                  // the next panel column lives in shared memory
+                double2* cp = reinterpret_cast<double2*>(myrow + P0 + 8 + 2 * q);
+                double2 c = *cp;
+                const double b0 = bcol[8 * (p + 1) * LD + q], b1 = bcol[8 * (p + 1) * LD + q + 4];
+                dmma(c.x, c.y, a0, b0);
+                dmma(c.x, c.y, a1, b1);
+                *cp = c;
             }
-        } else {
-            switch (p) {
-                case 0: if constexpr (0 <= NR - 3) rows_update<G, 0>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 1: if constexpr (1 <= NR - 3) rows_update<G, 1>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 2: if constexpr (2 <= NR - 3) rows_update<G, 2>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 3: if constexpr (3 <= NR - 3) rows_update<G, 3>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 4: if constexpr (4 <= NR - 3) rows_update<G, 4>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 5: if constexpr (5 <= NR - 3) rows_update<G, 5>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 6: if constexpr (6 <= NR - 3) rows_update<G, 6>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 7: if constexpr (7 <= NR - 3) rows_update<G, 7>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 8: if constexpr (8 <= NR - 3) rows_update<G, 8>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 9: if constexpr (9 <= NR - 3) rows_update<G, 9>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 10: if constexpr (10 <= NR - 3) rows_update<G, 10>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 11: if constexpr (11 <= NR - 3) rows_update<G, 11>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 12: if constexpr (12 <= NR - 3) rows_update<G, 12>(rt, bcol, myrow, a0, a1, chi, q); break;
-                case 13: if constexpr (13 <= NR - 3) rows_update<G, 13>(rt, bcol, myrow, a0, a1, chi, q); break;
-                default: break;
+            if (R == p + 1) {
+                if (q == 0) sm.yj[8 * R + g] = yR;             // ytilde of the next pivot rows is final
+                __syncwarp();
+                __threadfence_block();
+                named_arrive(1, 64);                           // hand the pivot tile to warp 0
+            } else {
+                switch (p) {                                   // tiles p+2 .. R of this row take the rank-8 update
+                    case 0: if constexpr (0 <= NR - 3) rows_update<G, 0>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 1: if constexpr (1 <= NR - 3) rows_update<G, 1>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 2: if constexpr (2 <= NR - 3) rows_update<G, 2>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 3: if constexpr (3 <= NR - 3) rows_update<G, 3>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 4: if constexpr (4 <= NR - 3) rows_update<G, 4>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 5: if constexpr (5 <= NR - 3) rows_update<G, 5>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 6: if constexpr (6 <= NR - 3) rows_update<G, 6>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 7: if constexpr (7 <= NR - 3) rows_update<G, 7>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 8: if constexpr (8 <= NR - 3) rows_update<G, 8>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 9: if constexpr (9 <= NR - 3) rows_update<G, 9>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 10: if constexpr (10 <= NR - 3) rows_update<G, 10>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 11: if constexpr (11 <= NR - 3) rows_update<G, 11>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 12: if constexpr (12 <= NR - 3) rows_update<G, 12>(rt, bcol, myrow, a0, a1, R, q); break;
+                    case 13: if constexpr (13 <= NR - 3) rows_update<G, 13>(rt, bcol, myrow, a0, a1, R, q); break;
+                    default: break;
+                }
             }
         }
         __syncthreads();                                       // next panel column and its pivot tile are in place
@@ -639,32 +647,21 @@ __device__ __forceinline__ void diag_pad_identity(SM& sm, int c0, int tid) {
             if (c >= c0) dst[d] = (m == c) ? 1.0 : 0.0;
         }
     }
-    if (tid >= c0 && tid < 8 * G::NR) sm.dinv[tid] = 1.0;
+    if (tid >= c0 && tid < 8 * G::NR) { sm.dinv[tid] = 1.0; sm.zs[tid] = 0.0; }      // padded rows: L = I, ytilde = 0
+    for (int d = 8 * c0 + tid; d < 64 * G::NR; d += G::NTH)   // L_pp of the padded tiles (c0 is a multiple of 8)
+        sm.lpp[d] = ((d >> 3) & 7) == (d & 7) ? 1.0 : 0.0;
 }
 
-// z_J = W ytilde_J as a DMMA matrix-vector product (ytilde in column 0 of the B operand), |z_J|^2 and sum log L_rr.
-// Warp w owns rows 8w..8w+7; k runs over the slabs 0..w/2 of sm.W (zeros above the diagonal are stored).
+// |z_J|^2 and sum log L_rr of the block, as fixed-order per-warp partial sums (sm.qpart / sm.lpart)
 template <class G, class SM>
-__device__ __forceinline__ void diag_solve(SM& sm, int warp, int lane) {
-    const int g = lane >> 2, q = lane & 3;
-    double za0 = 0.0, za1 = 0.0, zb0 = 0.0, zb1 = 0.0;
-    for (int s = 0; s <= (warp >> 1); s++) {
-        const double* base = sm.W + G::wslab(s) + (warp - 2 * s) * 128 + lane * 2;
-        const double2 f0 = *reinterpret_cast<const double2*>(base);
-        const double2 f1 = *reinterpret_cast<const double2*>(base + 64);
-        const double* yk = sm.yj + 16 * s + 2 * q;                 // f0 = W[.][16s + 2q], [.. + 1]; f1 the same 8 further
-        const double y0 = g == 0 ? yk[0] : 0.0, y1 = g == 0 ? yk[1] : 0.0, y2 = g == 0 ? yk[8] : 0.0, y3 = g == 0 ? yk[9] : 0.0;
-        dmma(za0, za1, f0.x, y0);
-        dmma(zb0, zb1, f0.y, y1);
-        dmma(za0, za1, f1.x, y2);
-        dmma(zb0, zb1, f1.y, y3);
-    }
-    const double z = za0 + zb0;                                // rows 8w+g, column 0: lanes with q == 0
+__device__ __forceinline__ void diag_sums(SM& sm, int warp, int lane) {
+    constexpr int NB = 8 * G::NR;
+    const int i = 32 * warp + lane;
     double z2 = 0.0, lg = 0.0;
-    if (q == 0) {
-        sm.zs[8 * warp + g] = z;
+    if (i < NB) {
+        const double z = sm.zs[i];
         z2 = z * z;
-        lg = -log(sm.dinv[8 * warp + g]);                      // log L_rr (identity padding gives exactly 0)
+        lg = -log(sm.dinv[i]);                                 // log L_rr (identity padding gives exactly 0)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -687,12 +684,13 @@ __device__ __forceinline__ void diag_solve(SM& sm, int warp, int lane) {
 //     as an A operand -- one 32-deep product per earlier warp column, after a named barrier of the warp row;
 //   * the warp's OWN four tile columns: substitution inside the registers.  In the tile-major layout a C fragment IS an
 //     A operand, so T_c feeds W_cc^T and X_c feeds the updates of the tiles to its right without leaving the registers;
-//     the four tile rows (mi) are independent chains.
+//     the four tile rows (mi) are independent chains.  Each 8 x 8 tile solve X_c L_cc^T = T_c is the product with the
+//     explicit inverse followed by one step of iterative refinement against L_cc (sm.lpp).
 // sm.W holds the operator in B-operand layout (mix_operator): W_cc in the diagonal tiles, L_JJ itself in the tiles
 // below.  acc enters as -S and leaves as X = L_IJ.  stag: 128-row staging block, written with X for the warps to the right.
 template <class G, int NG>
 __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __restrict__ stag, const double* __restrict__ Wm,
-                                             int wr, int wc, int lane) {
+                                             const double* __restrict__ Lpp, int wr, int wc, int lane) {
 #pragma unroll 1
     for (int c = 0; c < NG; c++) {
         if (wc == c) {
@@ -702,14 +700,27 @@ __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __r
                 const int C = 4 * c + ni;                                                 // tile column of the block
                 const double* bcol = Wm + G::wslab(C >> 1) - (C >> 1) * 256 + (C & 1) * 64 + lane * 2;   // tile (R, C) at bcol + 128 R
                 const double2 w = *reinterpret_cast<const double2*>(bcol + 128 * C);       // W_CC
-                double xd[4][2];
+                const double2 lp = *reinterpret_cast<const double2*>(Lpp + 64 * C + lane * 2);   // L_CC
+                double xd[4][2], rs[4][2];
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) {                                          // X = T W_CC^T = (-acc) W_CC^T
+                for (int mi = 0; mi < 4; mi++) {                                          // X0 = T W_CC^T = (-acc) W_CC^T
                     xd[mi][0] = 0.0; xd[mi][1] = 0.0;
                     dmma(xd[mi][0], xd[mi][1], -acc[mi][ni][0], w.x);
                 }
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], -acc[mi][ni][1], w.y);
+                // one step of iterative refinement (see panel_scale): R = T - X0 L_CC^T, X = X0 + R W_CC^T
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) {
+                    rs[mi][0] = -acc[mi][ni][0]; rs[mi][1] = -acc[mi][ni][1];
+                    dmma(rs[mi][0], rs[mi][1], -xd[mi][0], lp.x);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) dmma(rs[mi][0], rs[mi][1], -xd[mi][1], lp.y);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], rs[mi][0], w.x);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], rs[mi][1], w.y);
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++) { acc[mi][ni][0] = xd[mi][0]; acc[mi][ni][1] = xd[mi][1]; }
 #pragma unroll
@@ -772,9 +783,9 @@ __device__ __forceinline__ void lz_partials(const double (&acc)[4][4][2], const 
     }
 }
 
-// sm.W after the diagonal sweep is the full inverse W = L_JJ^{-1} (used once more for z_J = W ytilde_J); its diagonal
-// 8 x 8 tiles are the inverses of the pivot tiles.  Overwrite the tiles below the diagonal with L_JJ itself (lower
-// triangle of the workspace M = sm.regionA, row-major): the operator trsm_inplace expects.
+// After the diagonal sweep the diagonal 8 x 8 tiles of sm.W hold the pivot-tile inverses W_pp.  Fill the tiles below
+// the diagonal with L_JJ itself (lower triangle of the workspace M = sm.regionA, row-major): the operator that
+// trsm_inplace and diag_solve_subst expect.
 template <class G, class SM>
 __device__ __forceinline__ void mix_operator(SM& sm, int tid) {
     constexpr int NB = 8 * G::NR;
@@ -961,9 +972,8 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 TICK(4);
             }
             if (sm.fail) return false;
-            diag_solve<Geo128>(sm, warp, lane);                         // z_J = W ytilde_J, |z_J|^2, sum log diag
-            __syncthreads();                                            // every warp has read the full inverse
-            mix_operator<Geo128>(sm, tid);                              // L_JJ below the diagonal groups: two-level TRSM operator
+            mix_operator<Geo128>(sm, tid);                              // L_JJ below the pivot-tile inverses: the operator of trsm_inplace
+            diag_sums<Geo128>(sm, warp, lane);                          // |z_J|^2 (z_J came out of the sweep), sum log diag
             if (pf) sm.rowv[tid] = pv;                                  // row side of the first block below
             fence_async_smem();
             __syncthreads();
@@ -1003,7 +1013,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             TICK(7);
             if (pf) sm.rowv[tid] = pv;                             // row side of the next block
             if (rowact) {
-                trsm_inplace<Geo128, 4>(acc, sm.regionA, sm.W, wr, wc, lane);      // L_IJ L_JJ^T = S by substitution, acc: -S -> L_IJ
+                trsm_inplace<Geo128, 4>(acc, sm.regionA, sm.W, sm.lpp, wr, wc, lane);      // L_IJ L_JJ^T = S by substitution, acc: -S -> L_IJ
                 lz_partials(acc, sm.zs, sm.red, BS, wr, wc, lane);                 // L_IJ z_J, per warp column
                 // stored as each warp finishes: warps with little to do overlap their stores with the others' DMMAs
                 store_tile_frag<false>(lbase + ((size_t)(I * (I - 1) / 2) + J) * BLKD, acc, 32 * wr, 32 * wc, lane);
@@ -1058,7 +1068,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             // (or to a CTA that is computing, not waiting), so they cannot cycle; the cluster launch guarantees that all
             // CTAs of the group are resident.  A failed pivot raises `fail`, which every wait also watches.
             double* const wg = prm.wg + (size_t)slot * prm.wg_stride;             // WBUFS x [W | z], then qcol[], lcol[]
-            double* const qcol = wg + WBUFS * (W_DOUBLES + BS);
+            double* const qcol = wg + WBUFS * WX_DOUBLES;
             double* const lcol = qcol + prm.tcap;
             int* const ctr = prm.cctr + (size_t)slot * cctr_ints(prm.tcap);
             int* const failflag = ctr;                                             // a pivot failed somewhere
@@ -1078,14 +1088,16 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 return ok;
             };
             auto publish_w = [&](const int buf) {
-                double* dst = wg + (size_t)buf * (W_DOUBLES + BS);
+                double* dst = wg + (size_t)buf * WX_DOUBLES;
                 for (int i = tid; i < W_DOUBLES / 2; i += NT) reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(sm.W)[i];
                 if (tid < BS) dst[W_DOUBLES + tid] = sm.zs[tid];
+                for (int i = tid; i < 16 * 64; i += NT) dst[W_DOUBLES + BS + i] = sm.lpp[i];
             };
             auto fetch_w = [&](const int buf) {
-                const double* src = wg + (size_t)buf * (W_DOUBLES + BS);
+                const double* src = wg + (size_t)buf * WX_DOUBLES;
                 for (int i = tid; i < W_DOUBLES / 2; i += NT) reinterpret_cast<double2*>(sm.W)[i] = __ldcg(reinterpret_cast<const double2*>(src) + i);
                 if (tid < BS) sm.zs[tid] = __ldcg(src + W_DOUBLES + tid);
+                for (int i = tid; i < 16 * 64; i += NT) sm.lpp[i] = __ldcg(src + W_DOUBLES + BS + i);
             };
             // column 0: every CTA forms the first diagonal block itself (no accumulate, nothing to wait for)
             stage_points(sm.colv, vt, prm.npad_max, 0, tid);

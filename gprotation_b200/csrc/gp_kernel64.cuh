@@ -32,6 +32,7 @@ struct Smem2 {
     double yj[BC];
     double dinv[BC];
     double wt[128];
+    double lpp[8 * 64];           // 8 x 8 diagonal tiles of L_JJ (refinement of the tile solves)
     double lpart[8];
     double qpart[8];
     double etab[64];
@@ -43,6 +44,8 @@ struct Smem2 {
     int prob;
     int fail;
 };
+
+static_assert(2 * (sizeof(Smem2) + 1024) <= 233472, "two CTAs of gp_lnlike64_kernel must fit one SM's 228 KB of shared memory");
 
 __device__ __forceinline__ int w2_slab_off(int s) { return 128 * s * (9 - s); }      // slab s keeps row groups 2s..7
 __device__ __forceinline__ int w2_off(int c, int m) {
@@ -240,9 +243,8 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                     __syncthreads();
                 }
                 if (sm.fail) { failed = true; break; }
-                diag_solve<Geo64>(sm, warp, lane);
-                __syncthreads();
                 mix_operator<Geo64>(sm, tid);
+                diag_sums<Geo64>(sm, warp, lane);
                 if (J + 1 < T) stage_points2(sm.rowv, SR, vt, prm.npad_max, (J + 1) * BC, SR, tid);
                 fence_async_smem();
                 __syncthreads();
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                     if (tid < SR) sm.rowv[2 * SR + tid] = pv1;
                 }
                 if (rowact) {
-                    trsm_inplace<Geo64, 2>(acc, sm.regionA, sm.W, wr, wc, lane);     // L L_JJ^T = S by substitution, acc: -S -> L
+                    trsm_inplace<Geo64, 2>(acc, sm.regionA, sm.W, sm.lpp, wr, wc, lane);     // L L_JJ^T = S by substitution, acc: -S -> L
                     lz_partials(acc, sm.zs, sm.red, SR, wr, wc, lane);
                     const int Ib = I + (wr >> 1);                  // this warp's block row
                     store_tile_frag<false, SLAB2>(lbase + ((size_t)(Ib * (Ib - 1) / 2) + J) * BLK2, acc, 32 * (wr & 1), 32 * wc, lane);

@@ -478,7 +478,7 @@ int plan_launch(gprot_ctx* ctx, const ProblemList& pl, LaunchPlan& lp) {
 }
 
 constexpr int TCAP = 1024;                                   // block columns the cluster kernels can track (N <= 131072)
-constexpr size_t WG_STRIDE = WBUFS * (size_t)(W_DOUBLES + BS) + 2 * TCAP;
+constexpr size_t WG_STRIDE = WBUFS * (size_t)WX_DOUBLES + 2 * TCAP;
 
 // factor scratch, per-point vectors and (cluster kernels) the W exchange buffers, grown on demand; may lower lp.slots to
 // what fits in device memory
