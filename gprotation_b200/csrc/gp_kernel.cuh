@@ -51,7 +51,6 @@ struct Smem {
     double zs[BS];                // z_J
     double yj[BS];                // ytilde_J
     double dinv[BS];              // 1 / diag(L_JJ)
-    double wt[128];               // inverse of the current / next 8 x 8 diagonal tile (double buffered)
     double lpp[16 * 64];          // the 8 x 8 diagonal tiles L_pp of L_JJ, row-major (= tile-major operand layout), zero above the diagonal
     double lpart[16];             // per-warp partial sums of log diag(L_JJ)
     double etab[64];              // 2^(j/64)
@@ -188,6 +187,16 @@ struct Geo128 {
     static constexpr int NTH = 512;       // threads of the CTA
     __device__ static __forceinline__ int wslab(int s) { return w_slab_off(s); }
     __device__ static __forceinline__ int woff(int c, int m) { return w_off(c, m); }
+    // Tile row of the sweep owned by warp w (1..15).  Warps 4, 8, 12 share their scheduler (and its FP64 pipe) with the
+    // pivot warp 0, whose latency chain is the critical path of the sweep: they get the rows that finish first (1, 2, 3).
+    // The other schedulers see rows {4,7,10,13}, {5,8,11,14}, {6,9,12,15}.
+    __device__ static __forceinline__ int row_of(int w) {
+#ifdef GPROT_NO_ROWPERM
+        return w;
+#else
+        return (w & 3) == 0 ? (w >> 2) : 3 + w - (w >> 2);
+#endif
+    }
 };
 
 // Store a warp's 32 x 32 C-fragment tile (acc[mi][ni][e] at row 8mi+g, col 8ni+2q+e) into a tile-major block at tile
@@ -403,11 +412,19 @@ __device__ __forceinline__ double rsqrt_pos(double d) {
 }
 
 // Pivot-tile factorisation without shuffles: every lane of the pivot warp holds the whole lower triangle and runs the
-// same elimination (the dependent chain is rsqrt -> scale -> one DFMA per pivot); lane b < 8 then forms column b of
-// the inverse by forward substitution.  Needs ~100 registers, which only the pivot warp's own loop can afford.
-// Outputs: W_pp (sm.wt[buf] and its place in sm.W), L_pp (sm.lpp), 1/diag (sm.dinv).
+// same elimination; lane b < 8 also forms column b of the inverse by forward substitution.  The dependent chain is
+// pivot -> rsqrt (MUFU + 5 FP64) -> scale -> one DFMA -> next pivot, 72 cycles per column (tools/chain_bench.cu); a warp
+// issues in order, so everything else is kept small and free of that chain:
+//   * inverse row j is w[j] = ri_j (delta_jb - sum_{m<j} l[j][m] w[m]): the sum only needs row j of L, which is final once
+//     column j-1 is done, so it is formed while rsqrt(d_j) is in flight and one multiplication per row is left behind it;
+//   * L_pp, sqrt(d_j) and 1/l_jj are values every lane has: they are stored with lane-independent addresses (all lanes
+//     write the same word with the same value) instead of being picked per lane with selects (the first round-2 version
+//     spent 105 of its 464 instructions on FSEL, formed the inverse after the elimination and indexed it by lane through
+//     local memory: 1413 cycles alone on an SM against ~580 for the chain).
+// Needs ~100 registers, which only the pivot warp's own loop can afford.  Outputs: W_pp (diagonal tile p of sm.W: the
+// operator of the panel and of the TRSM), L_pp (sm.lpp, zero above the diagonal: set once per kernel), 1/diag (sm.dinv).
 template <class G, class SM>
-__device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lane) {
+__device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int lane) {
     const double* Mp = sm.regionA + (8 * p) * G::LD + 8 * p;
     double l[8][8];
 #pragma unroll
@@ -419,48 +436,48 @@ __device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int buf, int lan
             if (2 * b2 + 1 <= a) l[a][2 * b2 + 1] = v.y;
         }
     }
-    double rinv[8];
-    double lcol[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // column (lane & 7) of L_pp, picked up as the columns are finished
-    double dsel = 1.0;                                         // pivot of that column
     const int b = lane & 7;
+    double w[8];                                               // column b of W_pp
+    double rinv[8];
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         const double d = l[j][j];
         if (!(d > 0.0) || !(d < DBL_MAX)) bad = true;
-        const double ri = rsqrt_pos(d);
+        const double ri = rsqrt_pos(d);                        // 1 / l_jj to ~1 ulp
         rinv[j] = ri;
-        dsel = (b == j) ? d : dsel;
+        if (j < 7) {                                           // the chain first: next pivot
+            l[j + 1][j] *= ri;
+            l[j + 1][j + 1] = fma(-l[j + 1][j], l[j + 1][j], l[j + 1][j + 1]);
+        }
+        double sj = (j == b) ? 1.0 : 0.0;                      // in the shadow of the rsqrt (operands final before it)
 #pragma unroll
-        for (int a = j + 1; a < 8; a++) l[a][j] *= ri;
+        for (int m = 0; m < j; m++) sj = fma(-l[j][m], w[m], sj);
+        w[j] = ri * sj;
+        double lj = d * ri;                                    // l_jj = sqrt(d) = d / sqrt(d), one Newton step: <= 1 ulp
+        l[j][j] = fma(fma(-lj, lj, d), 0.5 * ri, lj);
 #pragma unroll
-        for (int a = j + 1; a < 8; a++) lcol[a] = (b == j) ? l[a][j] : lcol[a];
+        for (int a = j + 2; a < 8; a++) l[a][j] *= ri;
 #pragma unroll
         for (int a = j + 1; a < 8; a++)
 #pragma unroll
-            for (int b = j + 1; b <= a; b++) l[a][b] = fma(-l[a][j], l[b][j], l[a][b]);
+            for (int c = j + 1; c <= a; c++)
+                if (!(a == j + 1 && c == j + 1)) l[a][c] = fma(-l[a][j], l[c][j], l[a][c]);
     }
-    // 1/l_jj: rinv is 1/sqrt(d) to ~1 ulp
-    double w[8];
+    {
+        double* lp = sm.lpp + 64 * p;
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-        double s = 0.0;
+        for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int m = 0; m < a; m++) s = fma(l[a][m], w[m], s);
-        w[a] = (a == b) ? rinv[a] : ((a > b) ? -rinv[a] * s : 0.0);
+            for (int k = 0; k <= a / 2; k++)
+                *reinterpret_cast<double2*>(lp + a * 8 + 2 * k) = make_double2(l[a][2 * k], (2 * k + 1 <= a) ? l[a][2 * k + 1] : 0.0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) *reinterpret_cast<double2*>(sm.dinv + 8 * p + 2 * k) = make_double2(rinv[2 * k], rinv[2 * k + 1]);
     }
     if (lane < 8) {
-        double* wt = sm.wt + 64 * buf;
-        double* lp = sm.lpp + 64 * p;
-        double ldiag = dsel * w[b];                            // l_bb = sqrt(d_b) = d_b / sqrt(d_b), one Newton step: <= 1 ulp
-        ldiag = fma(fma(-ldiag, ldiag, dsel), 0.5 * w[b], ldiag);
+        double* wp = sm.W + G::woff(8 * p, 8 * p);             // diagonal tile p: row-major inside the tile
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
-            wt[a * 8 + b] = w[a];
-            sm.W[G::woff(8 * p + a, 8 * p + b)] = w[a];
-            lp[a * 8 + b] = (a > b) ? lcol[a] : ((a == b) ? ldiag : 0.0);     // L_pp for the refinement of the tile solves
-        }
-        sm.dinv[8 * p + b] = w[b];
+        for (int a = 0; a < 8; a++) wp[a * 8 + b] = w[a];
     }
     if (bad && lane == 0) sm.fail = 1;
 }
@@ -490,11 +507,13 @@ __device__ __forceinline__ void rows_update(double (&rt)[G::NR][2], const double
     }
 }
 
-#ifdef DIAG_TS
-__device__ long long g_ts[16][8];
+#ifdef DIAG_TS   // tools/sweep_bench.cu: time stamps of the pivot warp (TS) and of the owner of tile row p+1 (TSR) per step
+__device__ long long g_ts[16][16];
 #define TS(p, k) do { if (lane == 0) g_ts[p][k] = clock64(); } while (0)
+#define TSR(p, k) do { if (lane == 0 && R == (p) + 1) g_ts[p][8 + (k)] = clock64(); } while (0)
 #else
 #define TS(p, k) do { } while (0)
+#define TSR(p, k) do { } while (0)
 #endif
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -508,13 +527,14 @@ __device__ __forceinline__ void row_sync(int wr, int count) {
     }
 }
 
-// X = M(R, p) L_pp^-T for one tile row below the pivot (R > p), rewritten in place.  Returns the A fragment of -X.
+// X = M(R, p) L_pp^-T for one tile row below the pivot (R > p), rewritten in place and stored in sm.W (the operator of
+// trsm_inplace: W_pp on the diagonal tiles, L_JJ below).  Returns the A fragment of -X.
 // The product with the explicit inverse W_pp is only a first guess X0: its backward error is eps * cond(L_pp), which
 // costs a digit where neighbouring points are strongly correlated (cond of an 8 x 8 tile reaches 1e7).  One step of
 // iterative refinement on the tensor pipe, X = X0 + (M - X0 L_pp^T) W_pp^T, brings the tile solve to the accuracy of a
 // substitution (tools/emulate_trsm.py; profiles/r02_trsm_emulation.log).
 template <class G, class SM>
-__device__ __forceinline__ void panel_scale(SM& sm, double* row, const double* wt, int p, int g, int q, double& a0, double& a1) {
+__device__ __forceinline__ void panel_scale(SM& sm, double* row, const double* wt, int R, int p, int g, int q, double& a0, double& a1) {
     const double x0 = row[q], x1 = row[q + 4];
     const double2 m = *reinterpret_cast<const double2*>(row + 2 * q);          // M[g][2q], M[g][2q+1]: C-fragment of the tile
     const double b0 = wt[g * 8 + q], b1 = wt[g * 8 + q + 4];
@@ -530,6 +550,8 @@ __device__ __forceinline__ void panel_scale(SM& sm, double* row, const double* w
     dmma(c0, c1, r1, wv.y);
     __syncwarp();
     *reinterpret_cast<double2*>(row + 2 * q) = make_double2(c0, c1);
+    // the finished tile L(R, p) also goes to its place in the operator of the column's solves (tile-major: the C fragment as is)
+    *reinterpret_cast<double2*>(sm.W + G::woff(8 * R + g, 8 * p + 2 * q)) = make_double2(c0, c1);
     __syncwarp();
     a0 = -row[q]; a1 = -row[q + 4];
 }
@@ -548,11 +570,12 @@ __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int
     const int g = lane >> 2, q = lane & 3;
     double* M = sm.regionA;
     if (warp == 0) {
-        tile8_factor_all<G>(sm, 0, 0, lane);
+        tile8_factor_all<G>(sm, 0, lane);
         __syncthreads();
         for (int p = 0; p < nsteps; p++) {
+            TS(p, 0);
             {                                                  // z_p = W_pp ytilde_p while the row warps scale their panel tiles
-                const double* wrow = sm.wt + 64 * (p & 1) + 8 * (lane & 7);    // row of W_pp, zero above the diagonal
+                const double* wrow = sm.W + G::woff(8 * p, 8 * p) + 8 * (lane & 7);    // row of W_pp, zero above the diagonal
                 double z = 0.0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) z = fma(wrow[k], sm.yj[8 * p + k], z);
@@ -564,13 +587,13 @@ __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int
             if (p == nsteps - 1) break;
             named_sync(1, 64);                                 // pivot tile (p+1, p+1) is final
             TS(p, 3);
-            tile8_factor_all<G>(sm, p + 1, (p + 1) & 1, lane);
+            tile8_factor_all<G>(sm, p + 1, lane);
             TS(p, 4);
             __syncthreads();
         }
         return;
     }
-    const int R = warp;
+    const int R = G::row_of(warp);
     double* myrow = M + (8 * R + g) * LD;
     double rt[NR][2];                                          // rt[C] = C fragment of tile (R, C), 2 <= C <= R
 #pragma unroll
@@ -584,10 +607,13 @@ __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int
     __syncthreads();
     for (int p = 0; p < nsteps; p++) {
         const int P0 = 8 * p;
-        const double* wt = sm.wt + 64 * (p & 1);
+        const double* wt = sm.W + G::woff(8 * p, 8 * p);             // W_pp
         double a0 = 0.0, a1 = 0.0;                             // A fragment of -X(R)
-        if (R > p) panel_scale<G>(sm, myrow + P0, wt, p, g, q, a0, a1);
+        TSR(p, 0);
+        if (R > p) panel_scale<G>(sm, myrow + P0, wt, R, p, g, q, a0, a1);
+        TSR(p, 1);
         __syncthreads();                                       // X(C), C > p, and z_p visible to every warp
+        TSR(p, 2);
         if (p == nsteps - 1) break;
         if (R > p) {                                           // rows at or above the pivot are finished
             {                                                  // forward solve, fused: ytilde_R -= L(R, p) z_p
@@ -609,6 +635,7 @@ __device__ __forceinline__ void diag_factor_rows(SM& sm, int warp, int lane, int
                 if (q == 0) sm.yj[8 * R + g] = yR;             // ytilde of the next pivot rows is final
                 __syncwarp();
                 __threadfence_block();
+                TSR(p, 3);
                 named_arrive(1, 64);                           // hand the pivot tile to warp 0
             } else {
                 switch (p) {                                   // tiles p+2 .. R of this row take the rank-8 update
@@ -686,7 +713,7 @@ __device__ __forceinline__ void diag_sums(SM& sm, int warp, int lane) {
 //     A operand, so T_c feeds W_cc^T and X_c feeds the updates of the tiles to its right without leaving the registers;
 //     the four tile rows (mi) are independent chains.  Each 8 x 8 tile solve X_c L_cc^T = T_c is the product with the
 //     explicit inverse followed by one step of iterative refinement against L_cc (sm.lpp).
-// sm.W holds the operator in B-operand layout (mix_operator): W_cc in the diagonal tiles, L_JJ itself in the tiles
+// sm.W holds the operator in B-operand layout (written by the diagonal sweep): W_cc in the diagonal tiles, L_JJ itself in the tiles
 // below.  acc enters as -S and leaves as X = L_IJ.  stag: 128-row staging block, written with X for the warps to the right.
 template <class G, int NG>
 __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __restrict__ stag, const double* __restrict__ Wm,
@@ -783,19 +810,6 @@ __device__ __forceinline__ void lz_partials(const double (&acc)[4][4][2], const 
     }
 }
 
-// After the diagonal sweep the diagonal 8 x 8 tiles of sm.W hold the pivot-tile inverses W_pp.  Fill the tiles below
-// the diagonal with L_JJ itself (lower triangle of the workspace M = sm.regionA, row-major): the operator that
-// trsm_inplace and diag_solve_subst expect.
-template <class G, class SM>
-__device__ __forceinline__ void mix_operator(SM& sm, int tid) {
-    constexpr int NB = 8 * G::NR;
-    const double* M = sm.regionA;
-    for (int d = tid; d < NB * NB; d += G::NTH) {
-        const int c = d / NB, m = d - c * NB;
-        if ((c >> 3) > (m >> 3)) sm.W[G::woff(c, m)] = M[c * G::LD + m];
-    }
-}
-
 // ---------------------------------------------------------------- per-problem set-up shared by the kernels
 // exp(theta) and the derived constants (thread 0 of the CTA)
 __device__ __forceinline__ Hyp make_hyper(const double* th) {
@@ -853,6 +867,7 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
         sm.etab[tid] = EXP2_64TH[tid];
         for (int sl = 0; sl < 8; sl++) sm.W[w_slab_off(sl) + 64 + tid] = 0.0;   // tiles above the diagonal: never written again
     }
+    for (int i = tid; i < 16 * 64; i += NT) sm.lpp[i] = 0.0;         // L_pp tiles: only the lower triangles are ever written
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&sm.full[s], 1);
@@ -972,7 +987,6 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
                 TICK(4);
             }
             if (sm.fail) return false;
-            mix_operator<Geo128>(sm, tid);                              // L_JJ below the pivot-tile inverses: the operator of trsm_inplace
             diag_sums<Geo128>(sm, warp, lane);                          // |z_J|^2 (z_J came out of the sweep), sum log diag
             if (pf) sm.rowv[tid] = pv;                                  // row side of the first block below
             fence_async_smem();

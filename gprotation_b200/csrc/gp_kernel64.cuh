@@ -31,7 +31,6 @@ struct Smem2 {
     double zs[BC];
     double yj[BC];
     double dinv[BC];
-    double wt[128];
     double lpp[8 * 64];           // 8 x 8 diagonal tiles of L_JJ (refinement of the tile solves)
     double lpart[8];
     double qpart[8];
@@ -136,6 +135,8 @@ struct Geo64 {
     static constexpr int NTH = NT2;
     __device__ static __forceinline__ int wslab(int s) { return w2_slab_off(s); }
     __device__ static __forceinline__ int woff(int c, int m) { return w2_off(c, m); }
+    // tile row of the sweep owned by warp w (with two CTAs per SM a permutation like Geo128's measures no gain)
+    __device__ static __forceinline__ int row_of(int w) { return w; }
 };
 
 // ---------------------------------------------------------------- the kernel
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
         sm.etab[tid] = EXP2_64TH[tid];
         for (int sl = 0; sl < 4; sl++) sm.W[w2_slab_off(sl) + 64 + tid] = 0.0;    // tiles above the diagonal: never written again
     }
+    for (int i = tid; i < 8 * 64; i += NT2) sm.lpp[i] = 0.0;          // L_pp tiles: only the lower triangles are ever written
     if (tid == 0) {
         for (int s = 0; s < STG; s++) {
             mbar_init(&sm.full[s], 1);
@@ -243,7 +245,6 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                     __syncthreads();
                 }
                 if (sm.fail) { failed = true; break; }
-                mix_operator<Geo64>(sm, tid);
                 diag_sums<Geo64>(sm, warp, lane);
                 if (J + 1 < T) stage_points2(sm.rowv, SR, vt, prm.npad_max, (J + 1) * BC, SR, tid);
                 fence_async_smem();
