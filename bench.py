@@ -254,14 +254,22 @@ def parity_worker(path):
                       "ld": [r[2] for r in res], "c64": [r[3] for r in res]}))
 
 
-def parity_block(seed, n, theta, got, rows=64, kind="gp"):
+def parity_rows_of(B, rows=64):
+    """The rows of a B-row launch the parity block samples."""
+    return np.unique(np.linspace(0, B - 1, min(rows, B)).astype(int))
+
+
+def parity_block(seed, n, theta, got, rows=64, kind="gp", got_exact=None):
     """Rows of the bench launch against the oracle (north star: <= 1e-9 relative on lnlike).  Above cond(K) = 1e8 no fp64
     factorisation holds 1e-9; there the yardstick is the 80-bit evaluation and the scatter of two independent fp64 CPU
-    evaluations (LAPACK blocked, unblocked scalar Cholesky) around it."""
+    evaluations (LAPACK blocked, unblocked scalar Cholesky) around it.  got_exact: the same sampled rows evaluated by
+    the kernel in george's operation order (GPROT_EXACT_KERNEL), reported beside the bench kernel's value for every row
+    of the tail -- at eps * cond > 1e-9 the entry-level rounding of the covariance (a different +-1 ulp draw in the two
+    synthesis modes and in the oracle) is what separates correct fp64 evaluations."""
     import tempfile
 
     B = len(theta)
-    idx = np.unique(np.linspace(0, B - 1, min(rows, B)).astype(int))
+    idx = parity_rows_of(B, rows)
     with tempfile.TemporaryDirectory() as tmp:
         path = os.path.join(tmp, "parity_in.npz")
         np.savez(path, seed=seed, n=n, kind=kind, theta=theta[idx], got=np.asarray(got)[idx])
@@ -278,15 +286,21 @@ def parity_block(seed, n, theta, got, rows=64, kind="gp"):
     for k in np.nonzero(fin)[0]:
         if r["ld"][k] is not None:
             ld = r["ld"][k]
-            tail.append({"row": int(idx[k]), "cond": float(cond[k]), "rel_err_vs_oracle": abs(g[k] - ref[k]) / abs(ref[k]),
+            tail.append({"row": int(idx[k]), "cond": float(cond[k]), "eps_times_cond": float(2.220446049250313e-16 * cond[k]),
+                         "rel_err_vs_oracle": abs(g[k] - ref[k]) / abs(ref[k]),
                          "gpu_vs_80bit": abs(g[k] - ld) / abs(ld),
                          "lapack_vs_80bit": abs(ref[k] - ld) / abs(ld), "unblocked_f64_vs_80bit": abs(r["c64"][k] - ld) / abs(ld)})
+            if got_exact is not None:
+                tail[-1]["gpu_exact_mode_vs_80bit"] = abs(float(got_exact[k]) - ld) / abs(ld)
     rule = [bool(rel[j] <= 1e-9) for j in range(len(rel))]
+    rule_exact = list(rule)
     fk = list(np.nonzero(fin)[0])
     for v in tail:                                             # the tests' rule: flat 1e-9, else within 3x of the worse CPU fp64 answer
         j = fk.index(list(idx).index(v["row"]))
+        bound = max(1e-9, 3 * max(v["lapack_vs_80bit"], v["unblocked_f64_vs_80bit"]))
         if not rule[j]:
-            rule[j] = bool(v["gpu_vs_80bit"] <= max(1e-9, 3 * max(v["lapack_vs_80bit"], v["unblocked_f64_vs_80bit"])))
+            rule[j] = bool(v["gpu_vs_80bit"] <= bound)
+            rule_exact[j] = bool(v.get("gpu_exact_mode_vs_80bit", v["gpu_vs_80bit"]) <= bound)
     return {"rows": int(len(idx)), "finite_rows": int(fin.sum()),
             "finiteness_agrees": bool(np.array_equal(np.isfinite(g), fin)),
             "max_rel_err": float(rel.max()) if rel.size else None,
@@ -296,6 +310,7 @@ def parity_block(seed, n, theta, got, rows=64, kind="gp"):
             "frac_within_1e-9_cond_le_1e8": float(np.mean(rel[lo] <= 1e-9)) if lo.any() else None,
             "rows_cond_gt_1e8_or_missing_1e-9": tail,
             "rows_passing_test_rule": int(sum(rule)),
+            "rows_passing_test_rule_exact_mode": int(sum(rule_exact)) if got_exact is not None else None,
             "test_rule": "|gpu-oracle| <= 1e-9 |oracle|, else |gpu-80bit| <= max(1e-9, 3 max(|lapack-80bit|, |unblocked_f64-80bit|))",
             "against": "oracle/gp_oracle.py (dense NumPy/LAPACK restatement of the george path; george itself not installable: parity unpinned)"}
 
@@ -504,7 +519,9 @@ def run_ours(args):
     # ---- parity of the bench star itself (rank 0's star and proposals), after the timed region
     parity = None
     if rank == 0 and not args.no_parity:
-        parity = parity_block(rank, n, theta, res_dev, rows=args.parity_rows)
+        pidx = parity_rows_of(B, args.parity_rows)
+        parity = parity_block(rank, n, theta, res_dev, rows=args.parity_rows,
+                              got_exact=eng.lnlike_batch(np.ascontiguousarray(theta[pidx]), lc_id=lc, exact=True))
 
     # ---- the other BASELINE configs, each device-timed with the max over ranks
     extra = {}

@@ -239,9 +239,10 @@ __constant__ double EXP2_64TH[64] = {
 
 // exp(x) for finite x <= 0, <= 1 ulp: x = (64 k + j) ln2/64 + r, |r| <= ln2/128, exp = 2^k * T[j] * (1 + p(r)),
 // p of degree 5 in Estrin form (truncation r^6/720 < 3.5e-17).  Arguments below -700 give exactly 0 (exp(-700) ~ 1e-304
-// is zero against any diagonal this model can have); the compare is the only FP64 instruction spent on that, the select
-// is integer work.  (Measured: folding A and G into the exponent and reducing the argument with one FMA saves five
-// FP64 instructions per entry but costs 7x in entry accuracy and buys < 1 % -- the synthesis is not FP64-issue bound.)
+// is zero against any diagonal this model can have); that compare and the select are integer work.  19 FP64
+// instructions per covariance entry in all; the tile synthesis waits on the FP64 pipe (ncu: math-pipe throttle is its
+// first stall reason), so each of them counts.  (Measured: folding A and G into the exponent and reducing the argument
+// with one FMA saves five more but costs 7x in entry accuracy.)
 __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
     const double MAGIC = 0x1.8p+52;
     const double t = fma(x, 0x1.71547652b82fep+6, MAGIC);          // 64/ln2
@@ -257,7 +258,10 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ t
     const double res = fma(tj, pp, tj);
     int hi = __double2hiint(res) + ((ki >> 6) << 20);
     int lo = __double2loint(res);
-    if (!(x >= -700.0)) { hi = 0; lo = 0; }
+    // x <= -700 (x is never positive or NaN here: both terms of the exponent are <= 0 and finite or -inf): for negative
+    // doubles the order of the magnitudes is the order of the high words as unsigned integers -- an integer compare
+    // instead of one more instruction on the FP64 pipe, which the synthesis is bound by
+    if ((unsigned)__double2hiint(x) >= 0xC085E000u) { hi = 0; lo = 0; }
     return __hiloint2double(hi, lo);
 }
 
@@ -526,6 +530,15 @@ __device__ __forceinline__ void row_sync(int wr, int count) {
         default: asm volatile("bar.sync 5, %0;" ::"r"(count) : "memory"); break;
     }
 }
+// the producer's side of the same barrier: counted, not waited for
+__device__ __forceinline__ void row_arrive(int wr, int count) {
+    switch (wr) {
+        case 0: asm volatile("bar.arrive 2, %0;" ::"r"(count) : "memory"); break;
+        case 1: asm volatile("bar.arrive 3, %0;" ::"r"(count) : "memory"); break;
+        case 2: asm volatile("bar.arrive 4, %0;" ::"r"(count) : "memory"); break;
+        default: asm volatile("bar.arrive 5, %0;" ::"r"(count) : "memory"); break;
+    }
+}
 
 // X = M(R, p) L_pp^-T for one tile row below the pivot (R > p), rewritten in place and stored in sm.W (the operator of
 // trsm_inplace: W_pp on the diagonal tiles, L_JJ below).  Returns the A fragment of -X.
@@ -708,19 +721,30 @@ __device__ __forceinline__ void diag_sums(SM& sm, int warp, int lane) {
 // The block stays in the accumulators of the 4 x NG warp grid (warp (wr, wc): rows 32 wr.., columns 32 wc..), sixteen
 // independent 8 x 8 tiles per warp, so the DMMA pipe never waits on a dependent chain:
 //   * columns of OTHER warp columns (m < 4 wc): the finished X of warp (wr, c), c < wc, is read from the staging block
-//     as an A operand -- one 32-deep product per earlier warp column, after a named barrier of the warp row;
+//     as an A operand -- one 32-deep product per earlier warp column, after a named barrier of the warp row on which
+//     the producer only arrives: a warp leaves as soon as its own columns are solved and does its L z sums and its
+//     stores while the warps to its right still work (tools/trsm_bench.cu, profiles/r02_trsm_bench.log: the block
+//     epilogue against 21.5 k cycles of DMMA pipe time; giving the next solver the new X before the others was
+//     measured too and changes nothing -- the phases in which one warp per scheduler works alone run at 21 cycles per
+//     DMMA instead of 16.7 whatever their order);
 //   * the warp's OWN four tile columns: substitution inside the registers.  In the tile-major layout a C fragment IS an
 //     A operand, so T_c feeds W_cc^T and X_c feeds the updates of the tiles to its right without leaving the registers;
 //     the four tile rows (mi) are independent chains.  Each 8 x 8 tile solve X_c L_cc^T = T_c is the product with the
 //     explicit inverse followed by one step of iterative refinement against L_cc (sm.lpp).
 // sm.W holds the operator in B-operand layout (written by the diagonal sweep): W_cc in the diagonal tiles, L_JJ itself in the tiles
 // below.  acc enters as -S and leaves as X = L_IJ.  stag: 128-row staging block, written with X for the warps to the right.
+#ifdef TRSM_TS   // tools/trsm_bench.cu: per warp {own solve starts, solved, staged, fenced}
+__device__ long long g_trsm_ts[16][4];
+#endif
 template <class G, int NG>
 __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __restrict__ stag, const double* __restrict__ Wm,
                                              const double* __restrict__ Lpp, int wr, int wc, int lane) {
 #pragma unroll 1
-    for (int c = 0; c < NG; c++) {
+    for (int c = 0; c <= wc; c++) {
         if (wc == c) {
+#ifdef TRSM_TS
+            if (lane == 0) g_trsm_ts[threadIdx.x >> 5][0] = clock64();
+#endif
             // ---- own columns: tiles 4c .. 4c+3 of the block, acc = -T
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) {
@@ -728,26 +752,26 @@ __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __r
                 const double* bcol = Wm + G::wslab(C >> 1) - (C >> 1) * 256 + (C & 1) * 64 + lane * 2;   // tile (R, C) at bcol + 128 R
                 const double2 w = *reinterpret_cast<const double2*>(bcol + 128 * C);       // W_CC
                 const double2 lp = *reinterpret_cast<const double2*>(Lpp + 64 * C + lane * 2);   // L_CC
-                double xd[4][2], rs[4][2];
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++) {                                          // X0 = T W_CC^T = (-acc) W_CC^T
-                    xd[mi][0] = 0.0; xd[mi][1] = 0.0;
-                    dmma(xd[mi][0], xd[mi][1], -acc[mi][ni][0], w.x);
-                }
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], -acc[mi][ni][1], w.y);
-                // one step of iterative refinement (see panel_scale): R = T - X0 L_CC^T, X = X0 + R W_CC^T
+                const double nwx = -w.x, nwy = -w.y;
+                // acc holds -T.  X0 = T W_CC^T = (-T)(-W_CC)^T; then one step of iterative refinement (see panel_scale) with
+                // the residual kept negated in place of -T: -R = -T + X0 L_CC^T, X = X0 + R W_CC^T = X0 + (-R)(-W_CC)^T.
+                // No negated copies and no second set of accumulators: bitwise the same as forming R = T - X0 L_CC^T.
+                double xd[4][2];
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++) {
-                    rs[mi][0] = -acc[mi][ni][0]; rs[mi][1] = -acc[mi][ni][1];
-                    dmma(rs[mi][0], rs[mi][1], -xd[mi][0], lp.x);
+                    xd[mi][0] = 0.0; xd[mi][1] = 0.0;
+                    dmma(xd[mi][0], xd[mi][1], acc[mi][ni][0], nwx);
                 }
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) dmma(rs[mi][0], rs[mi][1], -xd[mi][1], lp.y);
+                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], acc[mi][ni][1], nwy);
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], rs[mi][0], w.x);
+                for (int mi = 0; mi < 4; mi++) dmma(acc[mi][ni][0], acc[mi][ni][1], xd[mi][0], lp.x);
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], rs[mi][1], w.y);
+                for (int mi = 0; mi < 4; mi++) dmma(acc[mi][ni][0], acc[mi][ni][1], xd[mi][1], lp.y);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], acc[mi][ni][0], nwx);
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) dmma(xd[mi][0], xd[mi][1], acc[mi][ni][1], nwy);
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++) { acc[mi][ni][0] = xd[mi][0]; acc[mi][ni][1] = xd[mi][1]; }
 #pragma unroll
@@ -759,11 +783,24 @@ __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __r
                     for (int mi = 0; mi < 4; mi++) dmma(acc[mi][n2][0], acc[mi][n2][1], xd[mi][1], b.y);
                 }
             }
-            if (c + 1 < NG) store_tile_frag<false>(stag, acc, 32 * wr, 32 * wc, lane);      // X for the warps to the right
-        }
-        if (c + 1 < NG) {
-            row_sync(wr, 32 * NG);
-            if (wc > c) {                                                                // -T_wc += X_c L_{wc,c}^T, 32 deep
+#ifdef TRSM_TS
+            if (lane == 0) g_trsm_ts[threadIdx.x >> 5][1] = clock64();
+#endif
+            if (c + 1 < NG) {                                                            // X for the warps to the right: counted on their
+                store_tile_frag<false>(stag, acc, 32 * wr, 32 * wc, lane);                // barrier, not waited for -- this warp is done
+#ifdef TRSM_TS
+                if (lane == 0) g_trsm_ts[threadIdx.x >> 5][2] = clock64();
+#endif
+                __threadfence_block();                                                   // and goes on to its L z sums and its stores
+#ifdef TRSM_TS
+                if (lane == 0) g_trsm_ts[threadIdx.x >> 5][3] = clock64();
+#endif
+                row_arrive(wr, 32 * (NG - c));                                           // while the others still solve
+            }
+        } else {
+            row_sync(wr, 32 * (NG - c));                                                 // X_c is in the staging block (the producer and
+            {                                                                            // the warps right of it: NG - c warps)
+                // -T_wc += X_c L_{wc,c}^T, 32 deep
 #pragma unroll
                 for (int ds = 0; ds < 2; ds++) {
                     const int s = 2 * c + ds;

@@ -53,6 +53,34 @@ CHAIN(k_f2f, x = (double)((float)x) + c)
 CHAIN(k_sqrt, x = sqrt(x) + c)
 CHAIN(k_div, x = c / x + c)
 
+// DMMA dependency through the accumulator (C -> D) and through the A operand (the result of one product is the left
+// factor of the next, as in the refined tile solves of the TRSM), ILP independent chains per warp
+template <int ILP, bool VIA_A>
+__global__ void k_dmma_chain(long long* out, double* sink, double b0) {
+    double c0[ILP], c1[ILP], a[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) { c0[i] = 1e-3 * threadIdx.x; c1[i] = 1e-3 * i; a[i] = 1.0 + 1e-6 * i; }
+    const double b = b0 + 1e-9 * threadIdx.x;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; it++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int i = 0; i < ILP; i++) {
+                if (VIA_A) { double d0 = 0.0, d1 = 0.0; dmma(d0, d1, c0[i], b); c0[i] = d0; c1[i] = d1; }
+                else dmma(c0[i], c1[i], a[i], b);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) s += c0[i] + c1[i];
+    sink[threadIdx.x] = s;
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
 __global__ void __launch_bounds__(32, 1) k_tile8(long long* out, double* dump, int reps) {
     extern __shared__ __align__(128) unsigned char raw[];
     Smem& sm = *reinterpret_cast<Smem*>(raw);
@@ -94,6 +122,14 @@ int main() {
     RUN(k_f2f, 2.0, 1.0, "F2F f64->f32->f64 + DADD");
     RUN(k_sqrt, 2.0, 1.0, "sqrt() + DADD");
     RUN(k_div, 2.0, 1.0, "c / x + DADD");
+#define RUND(ILP, VIA, label) k_dmma_chain<ILP, VIA><<<1, 32>>>(out, sink, 0.25); cudaDeviceSynchronize(); cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost); \
+    printf("%-46s %7.1f cycles per DMMA (%d chains per warp)\n", label, h / (1024.0 * ILP), ILP);
+    RUND(1, false, "DMMA -> DMMA through the accumulator");
+    RUND(4, false, "DMMA -> DMMA through the accumulator");
+    RUND(1, true, "DMMA -> DMMA through the A operand");
+    RUND(2, true, "DMMA -> DMMA through the A operand");
+    RUND(4, true, "DMMA -> DMMA through the A operand");
+    RUND(8, true, "DMMA -> DMMA through the A operand");
     cudaFuncSetAttribute(k_tile8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     double* dump; cudaMalloc(&dump, 1024);
     k_tile8<<<1, 32, sizeof(Smem)>>>(out, dump, 20);
