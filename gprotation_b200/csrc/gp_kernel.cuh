@@ -295,6 +295,11 @@ __device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], const SM& sm,
     const int g = lane >> 2, q = lane & 3;
     const Hyp& h = sm.hyp;
     double ti[4], si[4], ci[4];
+    double vdr[4] = {0.0, 0.0, 0.0, 0.0};                      // diagonal noise of this lane's rows: a global load, issued before
+    if (GENERAL && row0 == col0) {                             // the tile's arithmetic instead of inside it (diagonal tiles only)
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) vdr[mi] = vd[row0 + 8 * mi + g];
+    }
 #pragma unroll
     for (int mi = 0; mi < 4; mi++) {
         const int r = rl0 + 8 * mi + g;
@@ -317,7 +322,7 @@ __device__ __forceinline__ void synth_tile(double (&acc)[4][4][2], const SM& sm,
                 if (GENERAL) {
                     const int r = row0 + 8 * mi + g, c = col0 + 8 * ni + 2 * q + e;
                     const double d = ti[mi] - tj;
-                    if (r == c) nk = (nk - h.S) - vd[r];
+                    if (r == c) nk = (nk - h.S) - vdr[mi];
                     else if (white_off && d * d < h.thr) nk -= h.S;
                     if (r >= n || c >= n) nk = (r == c) ? -1.0 : 0.0;
                 }

@@ -163,6 +163,9 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
     __syncthreads();
 
     uint32_t it = 0;
+#ifdef GPROT_TIMING
+    long long tim_[16] = {0}, tlast_ = clock64();
+#endif
     const int slot = (int)blockIdx.x;
     double* const lbase = prm.lscratch + (size_t)slot * prm.lslot_stride;
     double* const vt = prm.vscratch + (size_t)slot * 5 * prm.npad_max;
@@ -180,6 +183,7 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
         __syncthreads();
         if (sm.prob >= prm.nprob) break;
         const int prob = prm.prob_order ? prm.prob_order[sm.prob] : sm.prob;
+        TICK(15);
 
         const int chunk = prm.prob_chunk[prob];
         const int n = prm.chunk_n[chunk];
@@ -203,6 +207,7 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
         for (int i = tid; i < npad + BC; i += NT2)               // one block of slack: the last super tile may reach past npad
             point_vectors(i, n, t, y, yerr, h, vt, vs, vc, vd, yw);
         __syncthreads();
+        TICK(0);
 
         double logdet = 0.0, quad = 0.0;
         double acc[4][4][2];
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
             stage_points2(sm.colv, BC, vt, prm.npad_max, J * BC, BC, tid);
             stage_points2(sm.rowv, SR, vt, prm.npad_max, J * BC, BC, tid);
             __syncthreads();
+            TICK(12);
             // ================= diagonal block (J, J): warps (0,0), (1,0), (1,1) of the upper half of the warp grid
             {
                 const int nreal = min(BC, n - J * BC);
@@ -221,8 +227,10 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                 const bool active = wr < 2 && wr >= wc && wr < ractJ;
                 if (tid == 0) prologue2<true>(sm, it, jrow, jrow, jrow, niter, false);
                 if (active) synth_tile<EXACT, true, SR, BC>(acc, sm, 32 * wr, 32 * wc, J * BC + 32 * wr, J * BC + 32 * wc, n, vd, white_off, lane);
+                TICK(1);
                 accumulate2<true>(sm, acc, it, jrow, jrow, jrow, niter, false, wr, wc, lane, active);
                 __syncthreads();
+                TICK(2);
                 if (wr < 2) {
                     double* M = sm.regionA;
 #pragma unroll
@@ -238,12 +246,14 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                 }
                 if (tid < BC) sm.yj[tid] = yw[J * BC + tid];
                 __syncthreads();
+                TICK(3);
                 const int nsteps = (nreal + 7) >> 3;
                 diag_factor_rows<Geo64>(sm, warp, lane, nsteps);
                 if (nsteps < 8) {
                     diag_pad_identity<Geo64>(sm, 8 * nsteps, tid);
                     __syncthreads();
                 }
+                TICK(4);
                 if (sm.fail) { failed = true; break; }
                 diag_sums<Geo64>(sm, warp, lane);
                 if (J + 1 < T) stage_points2(sm.rowv, SR, vt, prm.npad_max, (J + 1) * BC, SR, tid);
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                     quad += qs;
                     logdet += ls;
                 }
+                TICK(5);
             }
             if (tid == 0 && J + 1 < T) {
                 const int I = J + 1;
@@ -280,8 +291,10 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                     if (I * BC + SR <= n && !white_off) synth_tile<EXACT, false, SR, BC>(acc, sm, 32 * wr, 32 * wc, I * BC + 32 * wr, J * BC + 32 * wc, n, vd, white_off, lane);
                     else                                synth_tile<EXACT, true, SR, BC>(acc, sm, 32 * wr, 32 * wc, I * BC + 32 * wr, J * BC + 32 * wc, n, vd, white_off, lane);
                 }
+                TICK(6);
                 accumulate2<false>(sm, acc, it, a0, a1, jrow, niter, two, wr, wc, lane, rowact);
                 __syncthreads();                                   // stages drained: regionA becomes the X staging block; sm.rowv is free
+                TICK(7);
                 if (In < T) {
                     sm.rowv[tid] = pv0;                            // tid < 128: t, else sin (stride SR = 128)
                     if (tid < SR) sm.rowv[2 * SR + tid] = pv1;
@@ -292,18 +305,29 @@ __global__ void __launch_bounds__(NT2, 2) gp_lnlike64_kernel(const Params prm) {
                     const int Ib = I + (wr >> 1);                  // this warp's block row
                     store_tile_frag<false, SLAB2>(lbase + ((size_t)(Ib * (Ib - 1) / 2) + J) * BLK2, acc, 32 * (wr & 1), 32 * wc, lane);
                 }
+                TICK(8);
                 fence_async_smem();
                 __syncthreads();
+                TICK(9);
                 if (tid == 0 && In < T)
                     prologue2<false>(sm, it, lbase + (size_t)(In * (In - 1) / 2) * BLK2, lbase + (size_t)((In + 1) * In / 2) * BLK2, jrow, niter, In + 1 < T);
                 if (tid < 32 * ract) yw[I * BC + tid] = ycur - (sm.red[tid] + sm.red[SR + tid]);   // ytilde -= L z_J
+                TICK(10);
             }
+            // blocks of column J are first read (by TMA, the async proxy) in column J+1: one fence per column (fencing per
+            // super tile, each warp behind its own stores, was measured: the same on 300-point problems, 3-5 % slower at
+            // N = 600 ... 1000)
             __threadfence();
             fence_async();
             __syncthreads();
+            TICK(11);
         }
         if (tid == 0) prm.prob_out[prob] = finish_lnlike(quad, logdet, n, failed);
     }
+#ifdef GPROT_TIMING
+    if (tid == 0 && blockIdx.x == 0 && prm.timing)
+        for (int k = 0; k < 16; k++) prm.timing[k] = tim_[k];
+#endif
 }
 
 }  // namespace k64
