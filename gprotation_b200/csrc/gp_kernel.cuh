@@ -1067,6 +1067,9 @@ __global__ void __launch_bounds__(NT, 1) gp_lnlike_kernel(const Params prm) {
             accumulate<false>(sm, acc, it, irow, jrow, niter, wr, wc, lane, rowact);
             __syncthreads();                                       // stages drained: regionA becomes the X staging block; sm.rowv is free
             TICK(7);
+            // (Measured and rejected: letting the warps of the two left warp columns, which leave the block solve 12 - 20 k
+            // cycles before the last one, synthesise their tile of the next block row in that time.  Bitwise the same
+            // results, the same kernel time: the FP64 pipe is what the whole block is bound by, its order does not matter.)
             if (pf) sm.rowv[tid] = pv;                             // row side of the next block
             if (rowact) {
                 trsm_inplace<Geo128, 4>(acc, sm.regionA, sm.W, sm.lpp, wr, wc, lane);      // L_IJ L_JJ^T = S by substitution, acc: -S -> L_IJ
