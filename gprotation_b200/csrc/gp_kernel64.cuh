@@ -17,7 +17,10 @@ constexpr int BC = 64;            // block edge
 constexpr int NT2 = 256;          // 8 warps: 4 (rows of 32) x 2 (columns of 32) over the 128 x 64 super tile
 constexpr int SLAB2 = 1024;       // doubles in one 64 x 16 operand slab (8 KB)
 constexpr int BLK2 = 4096;        // doubles in one 64 x 64 block (4 slabs)
-constexpr int STG = 3;            // TMA pipeline depth (2 measures the same: the stream is not latency bound)
+constexpr int STG = 3;            // TMA pipeline depth (2 measures the same; a second ring of eight one-slab stages for the
+                                  // diagonal block, whose stages use 8 of their 24 KB, was measured too: 300-point chunks
+                                  // the same, N = 300 +3 % -- the slabs wait for the producer thread, which shares its
+                                  // scheduler's issue slots with the synthesis, not for the memory system)
 constexpr int STAGE_D = 3 * SLAB2;        // one stage: A slab of block row I, A slab of block row I+1, B slab of block row J
 constexpr int LDM2 = 68;          // pitch of the diagonal workspace (== 4 mod 16)
 constexpr int REGION2 = STG * STAGE_D;    // 72 KB: stages | 128 x 64 staging block (64 KB) | diagonal workspace (34 KB)
