@@ -155,6 +155,27 @@ def test_fit_emcee3_control_flow(tmp_path):
     assert g.batch_calls == calls + 1               # only the initial ensemble evaluation
 
 
+def test_results_file_is_the_reference_hdf_layout_where_pytables_exists(tmp_path):
+    """gprot/fit.py:24-41 writes results/{name}.h5 with pandas-HDF keys samples / lc / gp_prior (/ period_prior); downstream
+    scripts read them with pd.read_hdf (gprot/summary.py:38-56).  Runs wherever PyTables is installed (not in this image:
+    there the same tables go to .npz, covered by test_fit_emcee3_control_flow)."""
+    pytest.importorskip("tables")
+    import pandas as pd
+
+    from gprotation_b200.fit import write_samples
+
+    g = GaussModel(name='star9')
+    g.acf_prior = True
+    g.period_mixture = np.array([[0.7, 2.0, 0.1], [0.3, 2.7, 0.2]])
+    df = pd.DataFrame(np.random.RandomState(3).normal(size=(50, 5)), columns=list(g.param_names))
+    f = write_samples(g, df, resultsdir=str(tmp_path / 'results'))
+    assert f.endswith('star9.h5')
+    assert np.allclose(pd.read_hdf(f, 'samples').values, df.values) and list(pd.read_hdf(f, 'samples').columns) == list(g.param_names)
+    assert list(pd.read_hdf(f, 'gp_prior').columns) == ['mu', 'sigma']
+    assert set(pd.read_hdf(f, 'lc').columns) == {'x', 'y', 'yerr'}
+    assert list(pd.read_hdf(f, 'period_prior').columns) == ['w', 'mu', 'sigma']
+
+
 def test_lightcurve_front_end(tmp_path):
     d = write_aigrain_dataset(str(tmp_path / 'aigrain'), 2, baseline=300.0)
     lc = AigrainLightCurve(1, directory=d, sub=10, chunksize=300)
