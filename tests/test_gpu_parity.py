@@ -234,6 +234,25 @@ def test_full_config_batch_is_deterministic_and_consistent(engine):
     assert np.all(np.isfinite(full) | (full == -np.inf))
 
 
+def test_bench_star_rows_against_the_oracle(engine):
+    """The workload bench.py times (rank 0: synthetic_lightcurve(0, 2048, kind="gp"), proposals from sample_from_prior(1024,
+    seed=1000)): the full 1024-row launch, 16 rows spread over it against the oracle, in both synthesis modes.  (bench.py's
+    own `parity` block checks 64 rows of the same launch after the timed region; cond(K) of these 16 goes up to 1.2e7.)"""
+    n, B = 2048, 1024
+    t, y, yerr, _ = synthetic_lightcurve(0, n, kind="gp")
+    th = o.sample_from_prior(B, seed=1000)
+    engine.unregister_all()
+    lc = engine.register_lc(t, y, yerr)
+    full = engine.lnlike_batch(th, lc_id=lc)
+    idx = np.unique(np.linspace(0, B - 1, 16).astype(int))
+    ref = np.array([o.lnlike_function(th[i], t, y, yerr) for i in idx])
+    conds = [cond_of(th[i], t, yerr) for i in idx]
+    check(full[idx], ref, conds, "bench star, rows of the 1024-row launch", truth=lambda k: truths(th[idx[k]], t, y, yerr))
+    check(engine.lnlike_batch(th[idx], lc_id=lc, exact=True), ref, conds, "bench star, exact-mode kernel",
+          truth=lambda k: truths(th[idx[k]], t, y, yerr))
+    assert np.all(np.isfinite(full) | (full == -np.inf))
+
+
 def test_lnpost_batch_masks_rows_outside_the_prior(engine):
     t, y, yerr, _ = synthetic_lightcurve(4, 300, baseline=400.0)
     engine.unregister_all()
