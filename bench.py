@@ -416,10 +416,12 @@ def run_config5(args):
     """configs[4]: end-to-end chain through GPRotModel -> Emcee3Model -> Ensemble / Sampler, in a fresh process (its own engine)."""
     tool = os.path.join(ROOT, "tools", "bench_chain.py")
     out = {}
-    # the config as BASELINE.json states it (64 walkers, 300-point chunks), the same star without chunking, and the
-    # reference's default ensemble size (scripts/gprot-fit: --nwalkers 500) on the chunked layout
+    # the config as BASELINE.json states it (64 walkers, 300-point chunks), the same star without chunking, the
+    # reference's default ensemble size (scripts/gprot-fit: --nwalkers 500) on the chunked layout, and the stated config
+    # again with the chain driven from the host side of the C ABI instead of the Python sampler (gprot_chain_run)
     for label, extra_args in (("chunked_300", []), ("nochunks", ["--nochunks", "--steps", str(max(1, args.c5_steps // 10))]),
-                              ("chunked_300_500_walkers", ["--walkers", "500", "--steps", str(max(1, args.c5_steps // 10)), "--cpu-steps", "1"])):
+                              ("chunked_300_500_walkers", ["--walkers", "500", "--steps", str(max(1, args.c5_steps // 10)), "--cpu-steps", "1"]),
+                              ("chunked_300_native_driver", ["--native", "--cpu-steps", "1"])):
         try:
             r = subprocess.run([sys.executable, tool, "--steps", str(args.c5_steps), "--cpu-steps", "3"] + extra_args,
                                capture_output=True, text=True, timeout=900)

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint, c_void_p
+from ctypes import CFUNCTYPE, POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("GPROT_B200_LIB", "libgprot_b200.so"))
@@ -44,12 +44,27 @@ SIGNATURES = {
     "gprot_group_unregister_lc": (c_int, [c_void_p, c_int]),
     "gprot_group_lnpost_batch": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double,
                                          c_void_p, c_int, c_void_p, c_void_p, c_uint]),
+    "gprot_chain_run_fn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gprot_chain_run": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_void_p, c_int, c_int, c_int64, c_int,
+                                c_void_p, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gprot_chain_last_error": (c_char_p, []),
     "gprot_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "gprot_launch_count": (c_int64, [c_void_p]),
     "gprot_measure_dmma_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "gprot_debug_read_scratch": (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_void_p]),
     "gprot_debug_read_timing": (c_int, [c_void_p, c_void_p]),
 }
+
+
+
+class ChainMoves(Structure):
+    """gprot_chain_moves (include/gprot_b200.h): mixture weights and parameters of the native ensemble sampler."""
+    _fields_ = [(n, c_double) for n in ("w_stretch", "w_de", "w_snooker", "w_kde", "stretch_a", "de_sigma", "de_gamma0", "snooker_gamma", "kde_bw")]
+
+
+# gprot_lnpost_fn: void (*)(void *user, int64_t n, const double *theta, double *lnprior, double *lnlike)
+LNPOST_FN = CFUNCTYPE(None, c_void_p, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double))
 
 _lib = None
 

@@ -168,18 +168,25 @@ def _chain_length_in_autocorr_times(sampler, nburn, nwalkers, verbose):
 def fit_emcee3(mod, nwalkers=500, verbose=False, nsamples=5000, targetn=6,
                iter_chunksize=10, pool=None, overwrite=False,
                maxiter=100, sample_directory='mcmc_chains',
-               nburn=3, mixedmoves=True, resultsdir='results', seed=None, **kwargs):
+               nburn=3, mixedmoves=True, resultsdir='results', seed=None, native=None, **kwargs):
     """The reference's fit driver (gprot/fit.py:53-152), same arguments and behaviour: resume from the stored chain
     unless ``overwrite``; a 0.4 / 0.4 / 0.2 mixture of KDE, DE(1.0) and DE-snooker moves (KDE alone without
     ``mixedmoves``); blocks of ``iter_chunksize`` steps, at most ``maxiter`` of them, until the chain is ``targetn``
     autocorrelation times long after ``nburn`` of them are set aside; ``nsamples`` random draws from what is left,
     written with ``write_samples`` and returned as a DataFrame.  ``pool`` defaults to ``EnsemblePool``: every
     half-ensemble proposal set is ONE device launch (the reference's DefaultPool / schwimmbad pool evaluates one walker
-    per call).  ``seed`` (not in the reference) makes a run reproducible."""
+    per call).  ``seed`` (not in the reference) makes a run reproducible.  ``native`` (not in the reference; default: the
+    environment variable GPROT_NATIVE_CHAIN=1) runs the blocks through ``Sampler.run_native`` -- the same chain driven from
+    the host side of the C ABI (csrc/gprot_chain.cpp), with the library's own random stream."""
     import pandas as pd
 
     from . import sampler as em
 
+    import os
+
+    if native is None:
+        native = os.environ.get("GPROT_NATIVE_CHAIN", "0") not in ("", "0")
+    native = bool(native) and pool is None
     rs = np.random.RandomState(seed)
     store = _chain_store(mod, sample_directory)
     sampler = em.Sampler([(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)] if mixedmoves else em.KDEMove(),
@@ -204,7 +211,7 @@ def fit_emcee3(mod, nwalkers=500, verbose=False, nsamples=5000, targetn=6,
         blocks += 1
         if verbose:
             print("Iteration {0}...".format(blocks))
-        sampler.run(ensemble, iter_chunksize, progress=verbose)
+        sampler.run(ensemble, iter_chunksize, progress=verbose, native=native)
         try:
             tau_max, neff = _chain_length_in_autocorr_times(sampler, nburn, nwalkers, verbose)
         except em.AutocorrError:

@@ -476,7 +476,104 @@ class Sampler(object):
             i += 1
             yield ensemble
 
-    def run(self, ensemble, niter, progress=False, **kwargs):
+    # ---- the same chain without the interpreter between the launches (csrc/gprot_chain.cpp through the C ABI)
+    def _native_moves(self):
+        """gprot_chain_moves for this sampler's move mix, or None when a move has no native counterpart."""
+        from . import _lib
+
+        mv = _lib.ChainMoves()
+        for move, w in zip(self._moves, self._weights):
+            if not isinstance(move, RedBlueMove) or move.nsplits != 2 or move.randomize_split or move.live_dangerously:
+                return None
+            if type(move) is StretchMove:
+                mv.w_stretch += w
+                mv.stretch_a = float(move.a)
+            elif type(move) is DEMove:
+                mv.w_de += w
+                mv.de_sigma = float(move.sigma)
+                mv.de_gamma0 = -1.0 if move.gamma0 is None else float(move.gamma0)
+            elif type(move) is DESnookerMove:
+                mv.w_snooker += w
+                mv.snooker_gamma = float(move.gammas)
+            elif type(move) is KDEMove:
+                mv.w_kde += w
+                mv.kde_bw = -1.0 if move.bw_method is None else float(move.bw_method)
+            else:
+                return None
+        if len(set(type(m) for m in self._moves)) != len(self._moves):       # two moves of one kind with different parameters
+            return None
+        return mv
+
+    def run_native(self, ensemble, niter, store=True, thin=1):
+        """``run`` through gprot_chain_run: red-blue split, moves, acceptance rule and storage as in ``sample``, executed on
+        the host side of the C ABI -- a step is two likelihood launches and no interpreter time.  With a GPRotModel on a
+        single-device engine the library calls gprot_lnpost_batch itself; any other model with ``lnpost_batch`` is reached
+        through a callback.  The random stream is the library's (seeded from ``ensemble.random``): a different realisation
+        of the same chain than ``run`` gives.  Raises if the move mix has no native counterpart."""
+        from ctypes import POINTER, c_double, cast
+
+        from . import _lib
+
+        mv = self._native_moves()
+        if mv is None:
+            raise ValueError("this move mix has no native counterpart (use Sampler.run)")
+        lib = _lib.load()
+        nw, nd = ensemble.nwalkers, ensemble.ndim
+        nstore = (niter // thin) if store else 0
+        be = self.backend
+        if nstore:
+            be.extend(nstore, nw, nd)
+        coords = np.ascontiguousarray(ensemble._coords, dtype=np.float64)
+        lp = np.ascontiguousarray(ensemble._log_prior, dtype=np.float64)
+        ll = np.ascontiguousarray(ensemble._log_likelihood, dtype=np.float64)
+        nacc = np.zeros(nw, dtype=np.int64)
+        i0 = be.niter
+        ptr = lambda a: a.ctypes.data + i0 * a.strides[0] if nstore else None      # noqa: E731
+        chain_args = (coords.ctypes.data, lp.ctypes.data, ll.ctypes.data, ptr(be._coords), ptr(be._log_prior), ptr(be._log_likelihood),
+                      nacc.ctypes.data)
+        seed = int(ensemble.random.randint(0, 2 ** 31 - 1)) * 2 ** 31 + int(ensemble.random.randint(0, 2 ** 31 - 1))
+        model = ensemble.model
+        mod = getattr(model, "mod", None)
+        eng = None
+        if mod is not None and hasattr(mod, "_prior_args"):                # a GPRotModel: its engine (created on first use)
+            eng = mod.engine
+        import ctypes as _ct
+        if nd == 5 and eng is not None and hasattr(eng, "_ctx") and hasattr(mod, "_prior_args"):
+            b, mu, sig, mix = mod._prior_args()
+            mu, sig = np.ascontiguousarray(mu, dtype=np.float64), np.ascontiguousarray(sig, dtype=np.float64)
+            mixc = None if mix is None or len(mix) == 0 else np.ascontiguousarray(mix, dtype=np.float64).reshape(-1, 3)
+            rc = lib.gprot_chain_run(eng._ctx, int(mod._registered_id()), b.ctypes.data, mu.ctypes.data, sig.ctypes.data, float(mod.pmin),
+                                     float(mod.pmax), mixc.ctypes.data if mixc is not None else None, 0 if mixc is None else mixc.shape[0],
+                                     nw, int(niter), int(thin), _ct.byref(mv), seed, *chain_args)
+        else:
+            target = mod if mod is not None and hasattr(mod, "lnpost_batch") else None
+            if target is None:
+                raise ValueError("run_native needs a model with lnpost_batch")
+
+            def fn(user, n, theta, out_lp, out_ll):
+                th = np.ctypeslib.as_array(theta, shape=(n, nd))
+                a, c = target.lnpost_batch(th.copy(), return_parts=True)
+                np.ctypeslib.as_array(out_lp, shape=(n,))[:] = a
+                np.ctypeslib.as_array(out_ll, shape=(n,))[:] = c
+
+            cb = _lib.LNPOST_FN(fn)
+            rc = lib.gprot_chain_run_fn(cast(cb, _ct.c_void_p), None, nw, nd, int(niter), int(thin), _ct.byref(mv), seed, *chain_args)
+        if rc != 0:
+            raise RuntimeError(lib.gprot_chain_last_error().decode())
+        ensemble._coords[...] = coords
+        ensemble._log_prior[...] = lp
+        ensemble._log_likelihood[...] = ll
+        ensemble.acceptance[:] = False
+        if nstore:
+            be._accepted += nacc
+            be.niter += nstore
+        if hasattr(be, "save"):
+            be.save()
+        return ensemble
+
+    def run(self, ensemble, niter, progress=False, native=False, **kwargs):
+        if native:
+            return self.run_native(ensemble, niter, **kwargs)
         it = self.sample(ensemble, niter, **kwargs)
         if progress:
             try:

@@ -116,6 +116,32 @@ int gprot_group_lnpost_batch(gprot_group *grp, int64_t B, const double *theta, c
                              double pmax, const double *mixture, int k, double *out_lnprior,
                              double *out_lnlike, unsigned flags);
 
+/* The ensemble sampler of the reference's fit driver on the host side of the boundary (gprot/fit.py:82-98,123-135: an
+ * emcee3 Ensemble over Emcee3Model, Sampler(moves).run(ensemble, n) with KDEMove 0.4 / DEMove(1.0) 0.4 / DESnookerMove 0.2).
+ * Same red-blue split, moves and acceptance rule as gprotation_b200/sampler.py, without the interpreter between the two
+ * likelihood launches of a step.  Weights <= 0 switch a move off; parameters <= 0 take the defaults of sampler.py
+ * (stretch a = 2, DE gamma0 = 2.38 / sqrt(2 ndim), snooker gamma = 1.7, KDE bandwidth = Scott's factor).
+ * coords [nwalkers, ndim], lnprior / lnlike [nwalkers] hold the ensemble on entry (every walker finite) and on return;
+ * chain [nsteps / thin, nwalkers, ndim], chain_lnprior / chain_lnlike [nsteps / thin, nwalkers] (any of them NULL: not
+ * stored) receive the ensemble after every thin-th step, naccepted [nwalkers] is incremented on those steps.
+ * The random stream is the library's own (xoshiro256++): a native chain and a Python-driven one are different
+ * realisations of the same Markov chain.  Errors: non-zero status, text from gprot_chain_last_error (thread local). */
+typedef void (*gprot_lnpost_fn)(void *user, int64_t n, const double *theta, double *lnprior, double *lnlike);
+typedef struct gprot_chain_moves {
+    double w_stretch, w_de, w_snooker, w_kde;                     /* mixture weights (normalised by the library) */
+    double stretch_a, de_sigma, de_gamma0, snooker_gamma, kde_bw; /* move parameters */
+} gprot_chain_moves;
+/* any log-posterior: fn evaluates n proposals at a time (tests drive it with a Gaussian) */
+int gprot_chain_run_fn(gprot_lnpost_fn fn, void *user, int nwalkers, int ndim, int64_t nsteps, int thin,
+                       const gprot_chain_moves *moves, uint64_t seed, double *coords, double *lnprior, double *lnlike,
+                       double *chain, double *chain_lnprior, double *chain_lnlike, int64_t *naccepted);
+/* GPRotModel.lnpost of light curve lc_id through gprot_lnpost_batch (prior arguments as there), ndim = 5 */
+int gprot_chain_run(gprot_ctx *ctx, int lc_id, const double *bounds, const double *mu, const double *sigma, double pmin,
+                    double pmax, const double *mixture, int k, int nwalkers, int64_t nsteps, int thin,
+                    const gprot_chain_moves *moves, uint64_t seed, double *coords, double *lnprior, double *lnlike,
+                    double *chain, double *chain_lnprior, double *chain_lnlike, int64_t *naccepted);
+const char *gprot_chain_last_error(void);
+
 /* Measurement hooks (bench.py): device time of the last likelihood launch, CUDA events on the
  * launching stream; number of kernels launched by this context so far; FP64 tensor (DMMA) peak
  * of this device measured by a register-resident mma.sync.m8n8k4.f64 loop. */

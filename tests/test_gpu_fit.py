@@ -43,6 +43,34 @@ def test_chain_log_likelihoods_match_oracle(engine):
     assert np.all(np.isfinite(sam.get_log_probability()))
 
 
+def test_native_chain_on_the_gpu_model(engine, tmp_path):
+    """Sampler.run(native=True) on a GPRotModel: gprot_chain_run drives gprot_lnpost_batch from the host side of the ABI.
+    Two launches per step, every stored log-likelihood / log-prior is the oracle's at the stored coordinates, the ensemble
+    moves, and fit_emcee3(native=True) produces a posterior sample like the Python-driven fit."""
+    engine.unregister_all()
+    mod, (t, y, yerr, truth) = _model(engine)
+    rs = np.random.RandomState(3)
+    ens = em.Ensemble(Emcee3Model(mod), mod.sample_from_prior(32, seed=5), pool=EnsemblePool(), random=rs)
+    start = ens.coords.copy()
+    l0 = engine.launch_count()
+    sam = em.Sampler([(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)])
+    sam.run(ens, 15, native=True)
+    assert engine.launch_count() - l0 == 15 * 2 * 2
+    chunks = o.split_chunks(len(t), 150)
+    coords = sam.get_coords()
+    ll, lp = sam.backend.log_likelihood, sam.backend.log_prior
+    for it in (0, 7, 14):
+        for w in (0, 13, 31):
+            ref = o.lnlike(coords[it, w], t, y, yerr, chunks)
+            assert abs(ll[it, w] - ref) <= 1e-9 * abs(ref)
+            assert lp[it, w] == pytest.approx(o.lnprior(coords[it, w]), rel=1e-12)
+    assert np.array_equal(coords[-1], ens.coords) and not np.array_equal(coords[-1], start)
+    assert 0.0 < sam.acceptance_fraction.mean() < 1.0
+    df = fit_emcee3(mod, nwalkers=24, nsamples=100, targetn=2, iter_chunksize=20, maxiter=3, nburn=1, overwrite=True,
+                    sample_directory=str(tmp_path / "mcmc_chains"), resultsdir=str(tmp_path / "results"), seed=2, native=True)
+    assert list(df.columns) == list(mod.param_names) and len(df) > 0 and np.all(np.isfinite(df.values))
+
+
 def test_fit_emcee3_on_gpu_model_and_resume(engine, tmp_path):
     engine.unregister_all()
     mod, _ = _model(engine, n=300, chunksize=None, seed=22)      # --nochunks: one N x N problem per walker

@@ -83,6 +83,50 @@ def test_moves_leave_gaussian_invariant(move):
     assert g.batch_calls == 1 + 2 * 600             # initial ensemble + one launch per half-ensemble per step
 
 
+@pytest.mark.parametrize("move", ["stretch", "de", "snooker", "kde", "mixed"])
+def test_native_chain_leaves_gaussian_invariant(move):
+    """Sampler.run(native=True): the same chain driven by csrc/gprot_chain.cpp through gprot_chain_run_fn (here with a
+    callback into the Gaussian; on the GPU gprot_chain_run calls gprot_lnpost_batch itself).  Same invariance bar as the
+    Python-driven moves, same launch accounting, stored log-probabilities consistent with the stored coordinates."""
+    g = GaussModel()
+    rs = np.random.RandomState(11)
+    moves = {"stretch": em.StretchMove(), "de": em.DEMove(1.0), "snooker": em.DESnookerMove(), "kde": em.KDEMove(),
+             "mixed": [(em.KDEMove(), 0.4), (em.DEMove(1.0), 0.4), (em.DESnookerMove(), 0.2)]}[move]
+    ens = em.Ensemble(Emcee3Model(g), rs.multivariate_normal(np.zeros(5), g.C, size=64), pool=EnsemblePool(), random=rs)
+    sam = em.Sampler(moves)
+    sam.run(ens, 600, native=True)
+    c = sam.get_coords(flat=True, discard=100)
+    assert c.shape == (500 * 64, 5)
+    assert np.abs(c.mean(0)).max() < 0.35 * np.sqrt(np.diag(g.C)).max()
+    assert np.abs(np.cov(c.T) - g.C).max() < 0.3 * np.abs(g.C).max()
+    assert 0.02 < sam.acceptance_fraction.mean() < 0.98
+    assert g.single_calls == 0
+    assert g.batch_calls == 1 + 2 * 600             # initial ensemble + one launch per half-ensemble per step
+    last = sam.get_coords()[-1]
+    assert np.array_equal(last, ens.coords)
+    assert np.allclose(sam.get_log_probability()[-1], g.lnpost_batch(last), rtol=0, atol=1e-12)
+    # thinning and a second run appended to the same store
+    sam.run(ens, 40, native=True, thin=4)
+    assert sam.get_coords().shape == (610, 64, 5) and np.array_equal(sam.get_coords()[-1], ens.coords)
+
+
+def test_native_chain_refuses_what_it_cannot_mirror():
+    g = GaussModel()
+    rs = np.random.RandomState(3)
+    few = em.Ensemble(Emcee3Model(g), rs.randn(8, 5), pool=EnsemblePool(), random=rs)
+    with pytest.raises(RuntimeError):                # red-blue moves need nwalkers >= 2 ndim (as the Python path)
+        em.Sampler(em.DEMove(1.0)).run(few, 5, native=True)
+    ens = em.Ensemble(Emcee3Model(g), rs.randn(32, 5), pool=EnsemblePool(), random=rs)
+    with pytest.raises(ValueError):                  # a move mix without a native counterpart
+        em.Sampler(em.StretchMove(randomize_split=True)).run(ens, 5, native=True)
+    # proposals outside the support come back with lnprior = -inf and are never accepted
+    start = rs.uniform(38.0, 39.9, size=(32, 5))
+    edge = em.Ensemble(Emcee3Model(g), start, pool=EnsemblePool(), random=rs)
+    sam = em.Sampler(em.DEMove(1.0))
+    sam.run(edge, 50, native=True)
+    assert np.all(np.abs(sam.get_coords()) < 40) and np.all(np.isfinite(sam.get_log_probability()))
+
+
 def test_ensemble_rejects_zero_probability_start_and_out_of_support_moves():
     g = GaussModel()
     bad = np.zeros((16, 5))

@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--nochunks", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--native", action="store_true", help="drive the chain from the host side of the C ABI (Sampler.run_native)")
     a = ap.parse_args()
     cs = None if a.nochunks else a.chunksize
     t, y, yerr, truth = synthetic_lightcurve(a.seed, a.n, kind="harmonic")
@@ -65,11 +66,11 @@ def main():
 
     ens = em.Ensemble(Emcee3Model(mod), start, pool=EnsemblePool(), random=np.random.RandomState(a.seed))
     sam = em.Sampler(moves)
-    sam.run(ens, 5)                                              # warm-up: allocations, scipy.stats import
+    sam.run(ens, 5, native=a.native)                             # warm-up: allocations
     sam.reset()
     l0 = mod.engine.launch_count()
     t0 = time.perf_counter()
-    sam.run(ens, a.steps)
+    sam.run(ens, a.steps, native=a.native)
     mod.engine.sync()
     gpu_s = time.perf_counter() - t0
     launches = mod.engine.launch_count() - l0
@@ -102,7 +103,8 @@ def main():
     line = {
         "metric": "end-to-end emcee3-style chain wall clock", "unit": "s", "higher_is_better": False,
         "config": {"workload": "configs[4]: %d steps x %d walkers, N=%d, %s" % (a.steps, a.walkers, a.n,
-                   "one N x N problem (--nochunks)" if cs is None else "%d chunks of <= %d points" % (nchunk, cs))},
+                   "one N x N problem (--nochunks)" if cs is None else "%d chunks of <= %d points" % (nchunk, cs)),
+                   "driver": "gprot_chain_run (host C++ above the likelihood ABI)" if a.native else "gprotation_b200/sampler.py (Python)"},
         "value": gpu_s, "ms_per_step": 1e3 * gpu_s / a.steps, "gpu_launches": int(launches),
         "likelihood_evals": a.steps * a.walkers, "acceptance": float(sam.acceptance_fraction.mean()),
         "cpu_baseline": {"kind": "port", "cores": cores, "value": cpu_s_per_step * a.steps, "unit": "s",
