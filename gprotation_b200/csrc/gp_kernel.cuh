@@ -738,8 +738,11 @@ __device__ __forceinline__ void diag_sums(SM& sm, int warp, int lane) {
 //     explicit inverse followed by one step of iterative refinement against L_cc (sm.lpp).
 // sm.W holds the operator in B-operand layout (written by the diagonal sweep): W_cc in the diagonal tiles, L_JJ itself in the tiles
 // below.  acc enters as -S and leaves as X = L_IJ.  stag: 128-row staging block, written with X for the warps to the right.
-#ifdef TRSM_TS   // tools/trsm_bench.cu: per warp {own solve starts, solved, staged, fenced}
+#ifdef TRSM_TS   // tools/trsm_bench.cu -DTRSM_TS: per warp {own solve starts, solved, staged, fenced}
 __device__ long long g_trsm_ts[16][4];
+#define TRSM_STAMP(k) do { if (lane == 0) g_trsm_ts[threadIdx.x >> 5][k] = clock64(); } while (0)
+#else
+#define TRSM_STAMP(k) do { } while (0)
 #endif
 template <class G, int NG>
 __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __restrict__ stag, const double* __restrict__ Wm,
@@ -747,9 +750,7 @@ __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __r
 #pragma unroll 1
     for (int c = 0; c <= wc; c++) {
         if (wc == c) {
-#ifdef TRSM_TS
-            if (lane == 0) g_trsm_ts[threadIdx.x >> 5][0] = clock64();
-#endif
+            TRSM_STAMP(0);
             // ---- own columns: tiles 4c .. 4c+3 of the block, acc = -T
 #pragma unroll
             for (int ni = 0; ni < 4; ni++) {
@@ -788,18 +789,12 @@ __device__ __forceinline__ void trsm_inplace(double (&acc)[4][4][2], double* __r
                     for (int mi = 0; mi < 4; mi++) dmma(acc[mi][n2][0], acc[mi][n2][1], xd[mi][1], b.y);
                 }
             }
-#ifdef TRSM_TS
-            if (lane == 0) g_trsm_ts[threadIdx.x >> 5][1] = clock64();
-#endif
+            TRSM_STAMP(1);
             if (c + 1 < NG) {                                                            // X for the warps to the right: counted on their
                 store_tile_frag<false>(stag, acc, 32 * wr, 32 * wc, lane);                // barrier, not waited for -- this warp is done
-#ifdef TRSM_TS
-                if (lane == 0) g_trsm_ts[threadIdx.x >> 5][2] = clock64();
-#endif
+                TRSM_STAMP(2);
                 __threadfence_block();                                                   // and goes on to its L z sums and its stores
-#ifdef TRSM_TS
-                if (lane == 0) g_trsm_ts[threadIdx.x >> 5][3] = clock64();
-#endif
+                TRSM_STAMP(3);
                 row_arrive(wr, 32 * (NG - c));                                           // while the others still solve
             }
         } else {
