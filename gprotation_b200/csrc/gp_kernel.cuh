@@ -1,23 +1,26 @@
 // gp_kernel.cuh -- fused covariance synthesis + blocked fp64 Cholesky + forward solve, sm_100a.
 //
-// One persistent CTA (512 threads, 16 warps) per SM pulls (walker, chunk) problems from a
-// global queue.  For a problem of n points (padded with identity to Npad = T*128):
+// One persistent CTA (512 threads, 16 warps) per SM -- or a thread-block cluster of 2 / 4 / 8 CTAs per problem when a
+// launch has fewer problems than SMs -- pulls (walker, chunk) problems from a global queue.  For a problem of n points
+// (padded with identity to Npad = T*128):
 //
 //   for block column J = 0..T-1                         (left-looking, 128 x 128 blocks)
-//     S_JJ = K_JJ - sum_{k<J} L_Jk L_Jk^T               DMMA, operands streamed by TMA bulk copies
-//     L_JJ, W = L_JJ^{-1}  (8-wide micro panels, DMMA)  in shared memory, one sweep gives both
-//     z_J = W ytilde_J ; quad += |z_J|^2 ; logdet += 2 sum log diag(L_JJ)
+//     S_JJ = K_JJ - sum_{k<J} L_Jk L_Jk^T               DMMA, operands streamed by TMA bulk copies (mbarrier ring)
+//     L_JJ by an 8-wide right-looking sweep             pivot tiles factored and inverted by one warp, panels and trailing
+//                                                       tiles on the DMMA pipe; z_J = L_JJ^{-1} ytilde_J rides along
+//     quad += |z_J|^2 ; logdet += sum log diag(L_JJ)
 //     for I > J:
 //        S_IJ = K_IJ - sum_{k<J} L_Ik L_Jk^T            DMMA (the N^3/3 term)
-//        L_IJ = S_IJ W^T                                DMMA (TRSM as a GEMM with the inverse)
+//        L_IJ L_JJ^T = S_IJ                             substitution over 8-wide tile columns in the accumulators; only the
+//                                                       8 x 8 pivot tiles are inverted, every tile solve is refined once
 //        ytilde_I -= L_IJ z_J                           right-looking forward solve, fused
-//        store L_IJ (fragment-major) to the slot's scratch
-//   lnlike = -1/2 (quad + logdet + n log 2 pi)
+//        store L_IJ (tile-major) to the slot's scratch
+//   lnlike = -1/2 (quad + 2 logdet + n log 2 pi)
 //
-// K is never materialised: each 128 x 128 tile of it is synthesised from the time stamps and
-// the five hyper-parameters directly into the DMMA accumulator registers (C-fragment layout)
-// at the first (and only) touch of that tile.  Reference arithmetic being replaced:
-// gprot/model.py:328-356 (george kernel build + HODLR factor + lnlikelihood).
+// K is never materialised: each 128 x 128 tile of it is synthesised from the time stamps and the five hyper-parameters
+// directly into the DMMA accumulator registers (C-fragment layout) at the first (and only) touch of that tile.
+// Reference arithmetic being replaced: gprot/model.py:328-356 (george kernel build + HODLR factor + lnlikelihood).
+// DESIGN.md section 3 has the measured critical paths (tools/sweep_bench.cu, trsm_bench.cu, chain_bench.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,7 +36,7 @@ constexpr int BLKD = 16384;       // doubles in one 128 x 128 block (8 slabs)
 constexpr int STAGES = 4;         // TMA pipeline depth; one stage = A slab + B slab = 32 KB
 constexpr int LDM = 132;          // row pitch of the diagonal-block workspace (== 4 mod 16: conflict-free fragments)
 constexpr int REGION_A = 128 * LDM;   // doubles; >= STAGES * 2 * SLAB
-constexpr int W_DOUBLES = 9216;   // packed fragment-major lower triangle of W (72 KB)
+constexpr int W_DOUBLES = 9216;   // packed tile-major lower triangle of the solve operator (72 KB)
 constexpr int WBUFS = 4;          // cluster kernels: exchange buffers for W_J, z_J, L_pp (a CTA may run up to WBUFS - 1 columns ahead)
 constexpr int WX_DOUBLES = W_DOUBLES + BS + 16 * 64;   // one exchange buffer: W | z | L_pp tiles
 __host__ __device__ constexpr int cctr_ints(int tcap) { return 3 * tcap + 8; }   // [0] fail, [1] diagdone, [2..] row counters, rowdone, coldone
@@ -45,8 +48,9 @@ struct Hyp {
 };
 
 struct Smem {
-    double regionA[REGION_A];     // TMA stages | S_IJ staging (fragment-major) | diagonal workspace M (row-major)
-    double W[W_DOUBLES];          // L_JJ^{-1}, B-operand fragments, rows c >= 16*slab only
+    double regionA[REGION_A];     // TMA stages | X staging of the block solve (tile-major) | diagonal workspace M (row-major)
+    double W[W_DOUBLES];          // operator of the solves with L_JJ (tile-major B operands, rows c >= 16*slab only): W_pp = L_pp^{-1}
+                                  // on the diagonal 8 x 8 tiles, L_JJ itself below them
     double red[4 * BS];           // cross-warp partial sums of L_IJ z_J
     double zs[BS];                // z_J
     double yj[BS];                // ytilde_J
@@ -403,14 +407,15 @@ __device__ __forceinline__ void accumulate(Smem& sm, double (&acc)[4][4][2], uin
     }
 }
 
-// ---------------------------------------------------------------- diagonal block: L_JJ and W = L_JJ^{-1} in one sweep
-// Workspace M (row-major, pitch LDM) holds S_JJ in its lower triangle and zeros above.  Eliminating 8 columns at a
-// time, the lower triangle becomes L and -- treating the rows above the diagonal as the identity appended below S --
-// the strict upper triangle becomes L^{-T} (M[i][c] = W[c][i]); 1/diag(L) goes to sm.dinv.
+// ---------------------------------------------------------------- diagonal block: L_JJ by an 8-wide right-looking sweep
+// Workspace M (row-major, pitch LDM) holds S_JJ in its lower triangle and zeros above.  Eliminating 8 columns at a time:
 //
-// (i)   warp 0 factors the 8 x 8 diagonal tile and inverts it in registers;
-// (ii)  every other tile row of the panel is multiplied by the tile inverse (2 DMMAs per tile);
-// (iii) all tiles right of the panel receive the rank-8 update (2 DMMAs per tile).
+// (i)   warp 0 factors the 8 x 8 pivot tile and inverts it in registers (tile8_factor_all);
+// (ii)  every tile of the panel below it is solved against the pivot tile: product with the tile inverse, one step of
+//       iterative refinement (panel_scale), and stored both in M and in the operator of the block's later solves (sm.W);
+// (iii) all tiles right of the panel receive the rank-8 update (2 DMMAs per tile), held in registers by the warp that
+//       owns the tile row (diag_factor_rows).
+// Only the 8 x 8 pivot tiles are ever inverted; 1/diag(L) goes to sm.dinv, the pivot tiles themselves to sm.lpp.
 // 1/sqrt(d) for a positive, finite, normal d: MUFU.RSQ64H seed (2^-22.9) and one third-order correction
 // (error ~ (5/16) e^3 ~ 2^-70), branch free -- the 8 x 8 tile factorisation below is a pure latency chain.
 __device__ __forceinline__ double rsqrt_pos(double d) {
@@ -492,14 +497,13 @@ __device__ __forceinline__ void tile8_factor_all(SM& sm, int p, int lane) {
 }
 
 // ---------------------------------------------------------------- diagonal block, trailing tiles in registers
-// Same elimination as diag_factor (bitwise the same L and W), organised so that the rank-8 updates never touch shared
-// memory: warp R owns tile row R of the workspace (8 rows x 128 columns) and keeps its not-yet-eliminated tiles
-// (R, C), C > p, as DMMA accumulators.  Shared memory only carries the current panel column p (M(R, p), rewritten in
-// place with X(R) = M(R, p) W_pp^T), the next panel column (each warp stores tile (R, p+1) right after updating it) and
-// the 8 x 8 pivot tile.  Per step the block-wide work is two 8-byte fragment loads per tile instead of a 16-byte
-// load + store of every trailing tile (the in-place version was bound by shared-memory bandwidth, not by the DMMA
-// pipe); the critical path is the owner of tile row p+1: one tile update, then the pivot-tile factorisation.
-// Finished tiles of W = L_JJ^{-1} go straight to their B-operand position in sm.W (no conversion pass).
+// The rank-8 updates never touch shared memory: warp R owns tile row R of the workspace (8 rows x 128 columns) and keeps
+// its not-yet-eliminated tiles (R, C), C > p, as DMMA accumulators.  Shared memory only carries the current panel column
+// p (M(R, p), rewritten in place with X(R) = M(R, p) L_pp^-T), the next panel column (each warp stores tile (R, p+1)
+// right after updating it) and the 8 x 8 pivot tile.  Per step the block-wide work is two 8-byte fragment loads per tile
+// instead of a 16-byte load + store of every trailing tile (an in-place version was bound by shared-memory bandwidth,
+// not by the DMMA pipe); the critical path is the owner of tile row p+1: one tile update, then the pivot-tile
+// factorisation (DESIGN.md section 3 has the measured time line).
 // rank-8 update of the register tiles C = P+2 .. chi of one tile row with panel column P (a0, a1 = A fragment of -X(R));
 // the tile that becomes the next-but-one panel column (C = P+2) is parked in shared memory right after its update
 template <class G, int P>
