@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-2 evidence on one B200 with the final kernels: bitwise fingerprint against the library the parity campaigns ran on
-# (libgprot_b200_base.so = commit e58e67c), tests, bench lines, ncu launch list + full captures, shape / cluster sweeps,
+# Round-2 evidence on one B200 with the final kernels: bitwise fingerprint against a baseline library when one is in the
+# tree (libgprot_b200_base.so: build the baseline commit with GPROT_BUILD_VARIANT=base:), tests, bench lines, ncu launch list + full captures, shape / cluster sweeps,
 # phase timelines, microbenchmarks.  Everything lands in gpurun_out/ (copied to profiles/ by hand afterwards).
 # The parity campaigns themselves (tools/parity_campaign.py 400 41 / 11, five minutes each) are not repeated when the
 # fingerprint is bitwise identical.
