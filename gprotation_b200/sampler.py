@@ -550,14 +550,23 @@ class Sampler(object):
             if target is None:
                 raise ValueError("run_native needs a model with lnpost_batch")
 
+            failure = []
+
             def fn(user, n, theta, out_lp, out_ll):
-                th = np.ctypeslib.as_array(theta, shape=(n, nd))
-                a, c = target.lnpost_batch(th.copy(), return_parts=True)
-                np.ctypeslib.as_array(out_lp, shape=(n,))[:] = a
-                np.ctypeslib.as_array(out_ll, shape=(n,))[:] = c
+                if failure:                                   # an earlier call raised: the outputs stay -inf, nothing is accepted
+                    return
+                try:
+                    th = np.ctypeslib.as_array(theta, shape=(n, nd))
+                    a, c = target.lnpost_batch(th.copy(), return_parts=True)
+                    np.ctypeslib.as_array(out_lp, shape=(n,))[:] = a
+                    np.ctypeslib.as_array(out_ll, shape=(n,))[:] = c
+                except BaseException as exc:                  # an exception cannot cross the C frames: keep it, raise it below
+                    failure.append(exc)
 
             cb = _lib.LNPOST_FN(fn)
             rc = lib.gprot_chain_run_fn(cast(cb, _ct.c_void_p), None, nw, nd, int(niter), int(thin), _ct.byref(mv), seed, *chain_args)
+            if failure:
+                raise failure[0]
         if rc != 0:
             raise RuntimeError(lib.gprot_chain_last_error().decode())
         ensemble._coords[...] = coords

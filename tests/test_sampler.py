@@ -119,6 +119,17 @@ def test_native_chain_refuses_what_it_cannot_mirror():
     ens = em.Ensemble(Emcee3Model(g), rs.randn(32, 5), pool=EnsemblePool(), random=rs)
     with pytest.raises(ValueError):                  # a move mix without a native counterpart
         em.Sampler(em.StretchMove(randomize_split=True)).run(ens, 5, native=True)
+    # an exception raised by the model inside the callback surfaces after the call, it is not swallowed
+
+    class Boom(GaussModel):
+        def lnpost_batch(self, thetas, return_parts=False):
+            if self.batch_calls >= 3:
+                raise KeyError("boom")
+            return GaussModel.lnpost_batch(self, thetas, return_parts)
+
+    b = Boom()
+    with pytest.raises(KeyError):
+        em.Sampler(em.DEMove(1.0)).run(em.Ensemble(Emcee3Model(b), rs.randn(32, 5), pool=EnsemblePool(), random=rs), 20, native=True)
     # proposals outside the support come back with lnprior = -inf and are never accepted
     start = rs.uniform(38.0, 39.9, size=(32, 5))
     edge = em.Ensemble(Emcee3Model(g), start, pool=EnsemblePool(), random=rs)
